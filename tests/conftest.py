@@ -1,0 +1,69 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+class Golden:
+    def __init__(self):
+        with open(os.path.join(GOLDEN_DIR, "golden_v1.json")) as f:
+            self.meta = json.load(f)
+        self.arrays = np.load(os.path.join(GOLDEN_DIR, "golden_v1.npz"))
+        self.cases = {c["name"]: c for c in self.meta["cases"]}
+
+    def data(self, name):
+        keys = ("t", "rv", "rverr", "rhk", "sig_rhk", "bis", "sig_bis")
+        return {k: self.arrays["data/%s/%s" % (name, k)] for k in keys}
+
+    def K(self, case):
+        return None if case["K_key"] is None else self.arrays[case["K_key"]]
+
+    def resid(self, case):
+        return self.arrays[case["resid_key"]]
+
+    def by_framework(self, *frameworks):
+        return [c for c in self.meta["cases"] if c["framework"] in frameworks]
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return Golden()
+
+
+def rel_err(a, b):
+    if np.isinf(a) or np.isinf(b):
+        return 0.0 if a == b else np.inf
+    return abs(a - b) / max(abs(b), 1e-300)
+
+
+def assert_matrix_parity(K, Kref, tri=None, rtol=1e-12, floor=1e-6):
+    """max|dK|/max|K| <= rtol and per entry
+    |dK_ij| <= rtol * max(|K_ij|, floor * max|K|)."""
+    K = np.asarray(K)
+    Kref = np.asarray(Kref)
+    assert K.shape == Kref.shape
+    if tri == "lower":
+        mask = np.tril(np.ones(K.shape, dtype=bool))
+    elif tri == "upper":
+        mask = np.triu(np.ones(K.shape, dtype=bool))
+    else:
+        mask = np.ones(K.shape, dtype=bool)
+    d = np.abs(K - Kref)[mask]
+    ref = np.abs(Kref)[mask]
+    kmax = ref.max()
+    assert d.max() <= rtol * kmax, "max-norm %.3e" % (d.max() / kmax)
+    tol = rtol * np.maximum(ref, floor * kmax)
+    worst = (d / tol).max()
+    assert worst <= 1.0, "per-entry parity violated: worst |dK|/tol = %.3f" % worst
