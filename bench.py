@@ -1,0 +1,391 @@
+#!/usr/bin/env python3
+"""Headline benchmark: GP log-likelihood evaluations per second, FP64, n = 3N = 1500
+(BASELINE.json configs[2]: BIGgp_mcmc-style batch of 4096 hyper-parameter sets x
+N = 500 epochs, QuasiPeriodic kernel), on N GPUs of one box.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path (covariance build -> Cholesky -> solve ->
+log-det -> log-likelihood) over one batch of 4096 synthetic hyper-parameter sets
+per GPU (weak scaling: every rank evaluates its own 4096; the per-sample results
+are all-gathered over NCCL inside the timed region).  One JSON line on stdout.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "gp_loglike_evals_per_s"
+UNIT = "evals/s"
+
+
+def flops_per_eval(n):
+    return n ** 3 / 3.0 + n ** 2           # potrf + one triangular solve
+
+
+def build_bytes_per_eval(n):
+    return 4.0 * n * (n + 1)               # lower triangle incl. diagonal, FP64, written once
+
+
+def workload(args, rank):
+    from oracle import gp_oracle as go      # synthetic input generator only (seeded draws)
+    N = args.epochs
+    t, (rv, rhk, bis), (e1, e2, e3) = go.synthetic_series(N, seed=1)
+    H = go.synthetic_biggp_hypers(args.batch, seed=1 + rank)
+    return N, t, (rv, rhk, bis), (e1, e2, e3), H
+
+
+def config_dict(args, world):
+    return {"workload": "BIGgp QuasiPeriodic, N=%d epochs (n=%d), batch %d hyper-parameter sets per GPU"
+                        % (args.epochs, 3 * args.epochs, args.batch),
+            "framework": "BIGgp", "kernel": "QuasiPeriodic", "n_epochs": args.epochs,
+            "matrix_order": 3 * args.epochs, "per_gpu_batch": args.batch,
+            "global_batch": args.batch * world, "sharding": "batch over ranks, allgather of ll",
+            "l2_policy": "inputs larger than L2 (%.1f GB of matrices per step per GPU)"
+                         % (args.batch * (3 * args.epochs + 1) * ((3 * args.epochs + 15) // 16 * 16) * 8 / 1e9)}
+
+
+class ClockSampler(object):
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(prefix="mf_clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.out = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(gpu_index)], stdout=self.out,
+                                         stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.out.close()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        with open(self.path) as f:
+            for line in f:
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 8:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    smax.append(float(parts[2]))
+                    power.append(float(parts[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, parts[4:8]):
+                    if val == "Active":
+                        reasons.add(name)
+        os.unlink(self.path)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_evals(N, t, ys, errs, H, seconds, max_evals):
+    """The oracle's literal port of the reference's CPU path (17 N x N kernel
+    evaluations + scipy cho_factor/cho_solve per likelihood), timed on this
+    host's cores.  Returns (evals/s, evals done, values)."""
+    from oracle import gp_oracle as go
+    rv, rhk, bis = ys
+    e1, e2, e3 = errs
+    y = go.biggp_y(rv, rhk, bis)
+    go.biggp_loglike_literal("QuasiPeriodic", H[0], t, y, e1, e2, e3)      # BLAS thread start-up
+    vals = []
+    t0 = time.perf_counter()
+    while len(vals) < max_evals:
+        vals.append(go.biggp_loglike_literal("QuasiPeriodic", H[len(vals) % len(H)], t, y, e1, e2, e3))
+        if time.perf_counter() - t0 >= seconds:
+            break
+    dt = time.perf_counter() - t0
+    return len(vals) / dt, len(vals), np.array(vals)
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
+        return max(n) if n else 1
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  The
+    reference is pure Python and /root/reference does not travel to the GPU box, so
+    this arm times the oracle's literal port of it (oracle/gp_oracle.py), all host
+    threads, a bounded sample of the same workload per step."""
+    if rank != 0:
+        return
+    N, t, ys, errs, H = workload(args, 0)
+    from oracle import gp_oracle as go
+    rv, rhk, bis = ys
+    e1, e2, e3 = errs
+    y = go.biggp_y(rv, rhk, bis)
+    sample = args.ref_sample
+
+    def step(k):
+        for i in range(sample):
+            go.biggp_loglike_literal("QuasiPeriodic", H[(k * sample + i) % len(H)], t, y, e1, e2, e3)
+
+    for k in range(args.warmup):
+        step(k)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        step(args.warmup + k)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    cores = blas_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config_dict(args, world),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d of the %d hyper-parameter sets per step, numpy %s, "
+                                       "host cpu_count %s" % (sample, args.batch, np.__version__,
+                                                             os.cpu_count())},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_ours(args, rank, local_rank, world):
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py measures the CUDA path; no GPU is visible")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    from miniframe_b200 import kernels
+    from miniframe_b200.BIGgp import BIGgp
+    from miniframe_b200._engine import Engine
+    eng = Engine.get()
+    lib = eng.lib
+
+    N, t, (rv, rhk, bis), (e1, e2, e3), H = workload(args, rank)
+    n, B = 3 * N, args.batch
+    gp = BIGgp(kernels.QuasiPeriodic, [None, None, None], t=t, rv=rv, rverr=e1, rhk=rhk,
+               sig_rhk=e2, bis=bis, sig_bis=e3)
+    prob = gp._problem(N)
+    t_d = eng.tensor(t)
+    diag_d = eng.tensor(gp._diag_yerr())
+    hyper_d = eng.tensor(H)
+    resid_d = eng.tensor(gp.y[None, :])
+    ll_d = torch.empty(B, dtype=torch.float64, device=dev)
+    info_d = torch.empty(B, dtype=torch.int32, device=dev)
+    ll_all = torch.empty(B * world, dtype=torch.float64, device=dev)
+    ws, ws_bytes = eng.workspace(B, n)
+    ld, stride = eng.ld(n), eng.matrix_stride(n)
+    chunk = max(1, min(B, ws_bytes // (stride * 8)))
+    stream = eng.stream()
+
+    # ---- FP64 roofline denominators, measured here --------------------------------
+    peaks = {}
+    if rank == 0:
+        a = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+        b = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+        torch.matmul(a, b)
+        best = 1e9
+        for _ in range(5):
+            e0, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1_.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1_))
+        peaks["cublas_dgemm_4096_tflops"] = 2 * 4096 ** 3 / (best * 1e-3) / 1e12
+        peaks["dmma_probe_tflops"] = eng.probe_fp64(0, 20000)
+        peaks["dfma_probe_tflops"] = eng.probe_fp64(1, 20000)
+        del a, b
+
+    launches = [0]
+
+    def step(events=None):
+        for b0 in range(0, B, chunk):
+            nb = min(chunk, B - b0)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if events is not None else None
+            if ev:
+                ev[0].record()
+            st = lib.mf_build_cov(eng.handle, ctypes.byref(prob), nb, eng.ptr(t_d), eng.ptr(diag_d),
+                                  ctypes.c_void_p(hyper_d.data_ptr() + b0 * prob.hyper_len * 8), None, 0,
+                                  eng.ptr(ws), ld, stride, stream)
+            assert st == 0, lib.mf_last_error(eng.handle)
+            if ev:
+                ev[1].record()
+            st = lib.mf_potrf_loglike(eng.handle, nb, n, eng.ptr(ws), ld, stride, eng.ptr(resid_d), 0,
+                                      ctypes.c_void_p(ll_d.data_ptr() + b0 * 8),
+                                      ctypes.c_void_p(info_d.data_ptr() + b0 * 4), stream)
+            assert st == 0, lib.mf_last_error(eng.handle)
+            if ev:
+                ev[2].record()
+                events.append(ev)
+            launches[0] += 2
+        if world > 1:
+            dist.all_gather_into_tensor(ll_all, ll_d)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    events = []
+    launches[0] = 0
+    ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_a.record()
+    for _ in range(args.steps):
+        step(events)
+    ev_b.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    elapsed_ms = ev_a.elapsed_time(ev_b)
+    tt = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(tt.item())
+    value = world * B * args.steps / (elapsed_ms * 1e-3)
+    build_ms = sum(ev[0].elapsed_time(ev[1]) for ev in events) / len(events)
+    potrf_ms = sum(ev[1].elapsed_time(ev[2]) for ev in events) / len(events)
+    n_fail = int((info_d != 0).sum().item())
+    gpu_launches = launches[0]
+
+    # ---- end to end through the public API, host buffers -------------------------------
+    A_host = torch.from_numpy(np.ascontiguousarray(H)).pin_memory()
+    out_host = torch.empty(B * world, dtype=torch.float64).pin_memory()
+    resid_bytes = gp.y.nbytes
+
+    def e2e_step():
+        ll = gp.log_likelihood_batch(A_host)          # H2D of the hyper-parameters inside
+        if world > 1:
+            dist.all_gather_into_tensor(ll_all, ll)
+            out_host.copy_(ll_all, non_blocking=False)
+        else:
+            out_host.copy_(ll, non_blocking=False)    # D2H of the result
+
+    for _ in range(min(args.warmup, 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(tt.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline on this box's cores (N = 1 only), bounded sample ---------------
+    cpu = None
+    parity = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, done, vals = cpu_port_evals(N, t, (rv, rhk, bis), (e1, e2, e3), H, args.cpu_seconds, 64)
+        got = ll_d[:done].cpu().numpy()
+        parity = float(np.max(np.abs(got - vals) / np.abs(vals)))
+        cpu = {"value": rate, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+               "sample": "first %d of the %d hyper-parameter sets, oracle literal port "
+                         "(numpy %s + scipy LAPACK), host cpu_count %s"
+                         % (done, B, np.__version__, os.cpu_count())}
+
+    hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        pass
+    per_launch = min(chunk, B)
+    potrf_tflops = flops_per_eval(n) * per_launch / (potrf_ms * 1e-3) / 1e12
+    build_gbs = build_bytes_per_eval(n) * per_launch / (build_ms * 1e-3) / 1e9
+    fp64_peak = max(peaks.get("cublas_dgemm_4096_tflops", 0.0), peaks.get("dmma_probe_tflops", 0.0))
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args, world),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT,
+                "h2d_bytes_per_step": int(H.nbytes + resid_bytes), "d2h_bytes_per_step": int(B * 8 * world)},
+        "gpu_launches": gpu_launches,
+        "roofline": {"kernel": "mf_potrf_ll_kernel", "bound": "tensor", "achieved": potrf_tflops,
+                     "peak": fp64_peak, "unit": "TFLOP/s", "frac": potrf_tflops / fp64_peak,
+                     "traffic": None,
+                     "peak_source": "FP64 is not in MEASURED_PEAKS.json: max of cuBLAS DGEMM 4096^3 "
+                                    "(best of 5) and the DMMA register probe, both measured in this run",
+                     "ms_per_launch": potrf_ms, "evals_per_launch": per_launch,
+                     "flops_per_eval": flops_per_eval(n)},
+        "roofline_build": {"kernel": "mf_cov_build_kernel", "bound": "hbm", "achieved": build_gbs,
+                           "peak": hbm_peak, "unit": "GB/s", "frac": build_gbs / hbm_peak,
+                           "traffic": None, "peak_source": hbm_src, "ms_per_launch": build_ms,
+                           "bytes_per_eval": build_bytes_per_eval(n)},
+        "fp64_peaks_measured": peaks,
+        "cpu_baseline": cpu,
+        "parity_vs_cpu_port_max_rel": parity,
+        "non_pd_samples": n_fail,
+        "kernel_share": {"build": build_ms / (build_ms + potrf_ms), "potrf": potrf_ms / (build_ms + potrf_ms)},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--batch", type=int, default=4096, help="hyper-parameter sets per GPU per step")
+    ap.add_argument("--epochs", type=int, default=500, help="N; the matrix order is 3N")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-sample", type=int, default=4, help="likelihoods per step of the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d" % args.gpus)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

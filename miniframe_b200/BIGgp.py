@@ -1,0 +1,197 @@
+"""Rajpaul et al. (2015) framework on the B200 (reference: miniframe/BIGgp.py).
+
+Same constructor, same ``compute_matrix`` / ``log_likelihood`` /
+``minus_log_likelihood`` signatures and results as the reference class, plus
+``log_likelihood_batch`` for many hyper-parameter sets at once (what an MCMC
+ensemble asks for, reference examples/BIGgp_mcmc.py:47-64, 87-96).  The block
+covariance, the Cholesky factorisation, the solve and the log-determinant all
+run in the sm_100a kernels behind include/miniframe_b200.h.
+
+Reference behaviours kept on purpose:
+  Q1  white noise wn^2 sits on the diagonal of every block, off-diagonal ones too;
+  Q2  y = [rv, bis, rhk] (BIGgp.py:52) while the covariance blocks are ordered
+      [rv, rhk, bis] (BIGgp.py:256-265);
+  Q3  log_likelihood ignores its ``nugget`` argument (BIGgp.py:300).
+"""
+import numpy as np
+
+from . import _lib
+from ._base import NUGGET_VALUE, GPBase, _is_torch
+from .kernels import SquaredExponential
+
+
+class BIGgp(GPBase):
+    """GP over RV, log R'hk and BIS sharing one latent function and its derivative.
+
+    Parameters
+    ----------
+    kernel : class
+        ``kernels.QuasiPeriodic`` or ``kernels.SquaredExponential`` (the class itself)
+    means : list
+        three mean-function classes or None
+    t, rv, rverr, rhk, sig_rhk, bis, sig_bis : arrays
+    """
+    _framework = _lib.FRAMEWORK_BIGGP
+
+    def __init__(self, kernel, means, t, rv, rverr, rhk, sig_rhk, bis, sig_bis):
+        self.kernel = kernel
+        self._init_means(means)
+        self.dKdt1, self.dKdt2, self.ddKdt2dt1, self.dddKdt2ddt1, \
+            self.dddKddt2dt1, self.ddddKddt2ddt1 = self.kernel.__subclasses__()
+        self.t = t
+        self.rv = rv
+        self.rverr = rverr
+        self.rhk = rhk
+        self.sig_rhk = sig_rhk
+        self.bis = bis
+        self.sig_bis = sig_bis
+        self.L = 2
+        self.y = np.concatenate([rv, bis, rhk])
+        self.yerr = np.concatenate([rverr, sig_bis, sig_rhk])
+        self.tt = np.tile(t, self.L + 1)
+        span = np.ptp(np.asarray(self.t))        # ndarray.ptp is gone in NumPy 2
+        self.tplot = np.array([self.t + 1.5 * span * i for i in range(self.L + 1)]).flatten()
+
+    @classmethod
+    def from_rdb(cls, filename, kernel=SquaredExponential, means=None, **kwargs):
+        """Build from an .rdb file with columns t, rv, rverr, bis, rhk, sig_rhk
+        (reference BIGgp.py:60-100, whose final call drops ``means`` and cannot
+        run; here ``means`` defaults to three None)."""
+        skip = kwargs.pop('skiprows', 2)
+        kwargs.pop('unpack', None)
+        t, rv, rverr, bis, rhk, sig_rhk = np.loadtxt(filename, skiprows=skip, unpack=True, **kwargs)
+        t = np.linspace(0, 1, t.size)
+        biserr = 2 * rverr
+        rv, rverr = scale(rv, rverr)
+        bis, sig_bis = scale(bis, biserr)
+        rhk, sig_rhk = scale(rhk, sig_rhk)
+        means = [None, None, None] if means is None else means
+        return cls(kernel, means, t, rv, rverr, rhk, sig_rhk, bis, sig_bis)
+
+    # ---- parameter bookkeeping ------------------------------------------------
+    def _kernel_pars(self, a):
+        if self.kernel.__name__ == 'SquaredExponential':
+            l, wn, _, _, _, _, _ = a
+            return [l, wn]
+        elif self.kernel.__name__ == 'QuasiPeriodic':
+            lp, le, p, wn, _, _, _, _, _ = a
+            return [lp, le, p, wn]
+
+    def _scaling_pars(self, a):
+        """vc, vr, lc, bc, br"""
+        return a[-5:]
+
+    def _y_flat(self):
+        return self.y
+
+    def _problem(self, n_epochs, nugget=False, jitter=False):
+        kid = self._kernel_id()
+        p = _lib.Problem()
+        p.framework = _lib.FRAMEWORK_BIGGP_JITT if jitter else _lib.FRAMEWORK_BIGGP
+        p.kernel = kid
+        p.extra_kernel = _lib.KERNEL_NONE
+        p.n_series = 3
+        p.n_epochs = int(n_epochs)
+        p.hyper_len = _lib.KERNEL_NPAR[kid] + 5
+        p.extra_len = 3 if jitter else 0
+        p.nugget = NUGGET_VALUE if nugget else 0.0
+        return p
+
+    def _hyper_row(self, a):
+        a = np.asarray(a, dtype=float).ravel()
+        if self._kernel_pars(a) is None:
+            raise TypeError("kernel class %r is not supported" % self.kernel.__name__)
+        return a[None, :]
+
+    def _diag_yerr(self):
+        # block order [rv, rhk, bis]: BIGgp.py:256-258
+        return np.concatenate([np.asarray(self.rverr, dtype=float) ** 2 * np.ones(self.t.size),
+                               np.asarray(self.sig_rhk, dtype=float) ** 2 * np.ones(self.t.size),
+                               np.asarray(self.sig_bis, dtype=float) ** 2 * np.ones(self.t.size)])
+
+    def _diag(self, yerr):
+        if yerr:
+            return "diag_yerr", self._diag_yerr
+        return "diag_1e-12", lambda: np.full(3 * self.t.size, 1e-12)       # BIGgp.py:260-261
+
+    # ---- covariance -------------------------------------------------------------
+    def _matrix(self, a, x, diag, nugget=False, jitter=None):
+        """Full (3 len(x)) square for times x on the device, back as numpy."""
+        eng = self.engine
+        x = np.asarray(x, dtype=float)
+        prob = self._problem(x.size, nugget=nugget, jitter=jitter is not None)
+        hyper = eng.tensor(self._hyper_row(a))
+        extra = None if jitter is None else eng.tensor(np.asarray(jitter, dtype=float).ravel()[None, :3])
+        K = eng.build_cov(prob, eng.tensor(x), eng.tensor(diag), hyper, extra, full=True)
+        n = 3 * x.size
+        return K[0, :n, :n].cpu().numpy()
+
+    def _block(self, a, x, p, q):
+        n = np.asarray(x).size
+        K = self._matrix(a, x, np.zeros(3 * n))
+        return np.ascontiguousarray(K[p * n:(p + 1) * n, q * n:(q + 1) * n])
+
+    def k11(self, a, x):
+        """Equation 18 of Rajpaul et al. (reference BIGgp.py:172-181)."""
+        return self._block(a, x, 0, 0)
+
+    def k22(self, a, x):
+        """Equation 19 (BIGgp.py:184-190)."""
+        return self._block(a, x, 1, 1)
+
+    def k33(self, a, x):
+        """Equation 20 (BIGgp.py:193-202)."""
+        return self._block(a, x, 2, 2)
+
+    def k12(self, a, x):
+        """Equation 21 (BIGgp.py:205-212)."""
+        return self._block(a, x, 0, 1)
+
+    def k13(self, a, x):
+        """Equation 22 (BIGgp.py:215-224)."""
+        return self._block(a, x, 0, 2)
+
+    def k23(self, a, x):
+        """Equation 23 (BIGgp.py:227-234)."""
+        return self._block(a, x, 1, 2)
+
+    def compute_matrix(self, a, yerr=True, nugget=False):
+        """The (3N, 3N) covariance of equation 24 (reference BIGgp.py:237-278)."""
+        _, make = self._diag(yerr)
+        return self._matrix(a, self.t, make(), nugget=nugget)
+
+    # ---- likelihood ---------------------------------------------------------------
+    def log_likelihood(self, a, b, nugget=True):
+        """Marginal log-likelihood for kernel parameters ``a`` and mean
+        parameters ``b`` (reference BIGgp.py:281-312).  Returns -inf when the
+        covariance is not positive definite."""
+        self.mean_pars = b
+        hyper = self._hyper_row(a)
+        self._check_finite(hyper)
+        key, make = self._diag(True)
+        ll = self._batch_loglike(self._problem(self.t.size), key, make, hyper, None,
+                                 np.asarray(self._mean_pars, dtype=float)[None, :]
+                                 if self.mean_pars_size else None)
+        if np.isnan(ll[0]):
+            raise ValueError("array must not contain infs or NaNs")
+        return float(ll[0])
+
+    def minus_log_likelihood(self, a, b, nugget=True):
+        return -self.log_likelihood(a, b, nugget=True)
+
+    def log_likelihood_batch(self, A, Bm=None):
+        """log_likelihood for every row of ``A`` (B, 9 | 7) in one device pass.
+        ``Bm`` (B, mean_pars_size) holds the mean parameters per row when the
+        model has any.  numpy in -> numpy out; torch in -> device tensor out.
+        Rows whose covariance is not positive definite give -inf."""
+        if not _is_torch(A):
+            A = np.asarray(A, dtype=float)
+        key, make = self._diag(True)
+        return self._batch_loglike(self._problem(self.t.size), key, make, A, None, Bm)
+
+
+def scale(x, xerr, m=None, s=None):
+    """Remove the mean and divide by the standard deviation (BIGgp.py:645-651)."""
+    m = x.mean() if m is None else m
+    s = x.std() if s is None else s
+    return (x - m) / s, xerr / s

@@ -1,0 +1,195 @@
+"""Mean functions of the drop-in API (reference: miniframe/means.py).
+
+Protocol used by the GP classes (reference means.py:18-36, BIGgp.py:36-41,
+137-159): a class with ``_parsize``, ``initialize()`` returning an instance with
+all parameters 0, a mutable ``pars`` list, and ``__call__(t)``.  Means only
+produce the length-n residual r = y - m(t; b): O(N) host work next to the
+O(n^3) device work, so they stay in numpy.
+"""
+from functools import wraps
+
+import numpy as np
+
+__all__ = ['Constant', 'Linear', 'Parabola', 'Cubic', 'Keplerian']
+
+
+def array_input(f):
+    """Hand ``__call__`` an at-least-1-D array."""
+    @wraps(f)
+    def wrapped(self, t):
+        return f(self, np.atleast_1d(t))
+    return wrapped
+
+
+class MeanModel(object):
+    _parsize = 0
+
+    def __init__(self, *pars):
+        self.pars = list(pars)
+
+    def __repr__(self):
+        return "{0}({1})".format(self.__class__.__name__, ", ".join(map(str, self.pars)))
+
+    @classmethod
+    def initialize(cls):
+        return cls(*([0.] * cls._parsize))
+
+    def __add__(self, b):
+        return Sum(self, b)
+
+    def __radd__(self, b):
+        return self.__add__(b)
+
+
+class Sum(MeanModel):
+    def __init__(self, m1, m2):
+        self.m1, self.m2 = m1, m2
+
+    @property
+    def _parsize(self):
+        return self.m1._parsize + self.m2._parsize
+
+    @property
+    def pars(self):
+        return self.m1.pars + self.m2.pars
+
+    def initialize(self):
+        return
+
+    def __repr__(self):
+        return "{0} + {1}".format(self.m1, self.m2)
+
+    @array_input
+    def __call__(self, t):
+        return self.m1(t) + self.m2(t)
+
+
+class Constant(MeanModel):
+    """m(t) = c"""
+    _parsize = 1
+
+    def __init__(self, c):
+        MeanModel.__init__(self, c)
+
+    @array_input
+    def __call__(self, t):
+        return np.full(t.shape, self.pars[0])
+
+
+class Linear(MeanModel):
+    """m(t) = slope * (t - mean(t)) + intercept (the reference centres on t.mean())"""
+    _parsize = 2
+
+    def __init__(self, slope, intercept):
+        MeanModel.__init__(self, slope, intercept)
+
+    @array_input
+    def __call__(self, t):
+        return self.pars[0] * (t - t.mean()) + self.pars[1]
+
+
+class Parabola(MeanModel):
+    """m(t) = quad * t^2 + slope * t + intercept"""
+    _parsize = 3
+
+    def __init__(self, quad, slope, intercept):
+        MeanModel.__init__(self, quad, slope, intercept)
+
+    @array_input
+    def __call__(self, t):
+        return np.polyval(self.pars, t)
+
+
+class Cubic(MeanModel):
+    """m(t) = cub * t^3 + quad * t^2 + slope * t + intercept"""
+    _parsize = 4
+
+    def __init__(self, cub, quad, slope, intercept):
+        MeanModel.__init__(self, cub, quad, slope, intercept)
+
+    @array_input
+    def __call__(self, t):
+        return np.polyval(self.pars, t)
+
+
+class Sine(MeanModel):
+    """m(t) = amp * sin(2 pi t / P + phase) + displacement"""
+    _parsize = 4
+
+    def __init__(self, amp, P, phi, D):
+        MeanModel.__init__(self, amp, P, phi, D)
+
+    @array_input
+    def __call__(self, t):
+        amp, P, phi, D = self.pars
+        return amp * np.sin((2 * np.pi * t / P) + phi) + D
+
+
+def _eccentric_anomaly(M, e, iterations):
+    """Fixed-count iteration of the reference (means.py:160-168, 204-212): the
+    starting guess is the third-order series, each step is E += (M - M_k) /
+    (1 - e cos E) with M_k lagging one step behind."""
+    E0 = M + e * np.sin(M) + 0.5 * (e ** 2) * np.sin(2 * M)
+    M0 = E0 - e * np.sin(E0)
+    for _ in range(iterations):
+        aux = M - M0
+        E1 = E0 + aux / (1 - e * np.cos(E0))
+        M1 = E0 - e * np.sin(E0)
+        E0, M0 = E1, M1
+    return E0
+
+
+def _kepler_rv(t, P, K, e, w, T0, iterations=100):
+    M = 2 * np.pi * (t - T0) / P
+    E = _eccentric_anomaly(M, e, iterations)
+    nu = 2 * np.arctan(np.sqrt((1 + e) / (1 - e)) * np.tan(E / 2))
+    return K * (e * np.cos(w) + np.cos(w + nu))
+
+
+class oldKeplerian(MeanModel):
+    """Keplerian parametrised by the time of periastron T0: (P, K, e, w, T0)."""
+    _parsize = 5
+
+    def __init__(self, P, K, e, w, T0):
+        MeanModel.__init__(self, P, K, e, w, T0)
+
+    @array_input
+    def __call__(self, t):
+        P, K, e, w, T0 = self.pars
+        return _kepler_rv(t, P, K, e, w, T0)
+
+
+class Keplerian(MeanModel):
+    """Keplerian parametrised by the orbital phase: (P, K, e, w, phi, offset);
+    T0 = t[0] - P phi / (2 pi)."""
+    _parsize = 6
+
+    def __init__(self, P, K, e, w, phi, offset):
+        MeanModel.__init__(self, P, K, e, w, phi, offset)
+
+    @array_input
+    def __call__(self, t):
+        P, K, e, w, phi, offset = self.pars
+        T0 = t[0] - (P * phi) / (2. * np.pi)
+        return _kepler_rv(t, P, K, e, w, T0) + offset
+
+
+class TOI175keplerians(MeanModel):
+    """Three Keplerians (b, c, d) plus a constant; planet b iterates 500 times,
+    c and d 100 times, as in the reference (means.py:237, 255, 273)."""
+    _parsize = 16
+
+    def __init__(self, Pb, Kb, eb, wb, phib, Pc, Kc, ec, wc, phic, Pd, Kd, ed, wd, phid, C):
+        MeanModel.__init__(self, Pb, Kb, eb, wb, phib, Pc, Kc, ec, wc, phic,
+                           Pd, Kd, ed, wd, phid, C)
+
+    @array_input
+    def __call__(self, t):
+        p = self.pars
+        total = np.full(t.shape, p[-1])
+        rv = 0.0
+        for k, iters in ((0, 500), (1, 100), (2, 100)):
+            P, K, e, w, phi = p[5 * k:5 * k + 5]
+            T0 = t[0] - (P * phi) / (2. * np.pi)
+            rv = rv + _kepler_rv(t, P, K, e, w, T0, iterations=iters)
+        return rv + total

@@ -1,0 +1,312 @@
+"""GPU parity tests proper: the CUDA path, called through the drop-in classes and
+the C ABI, against the golden vectors of the unmodified reference and against the
+oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star):
+  covariance entries: max|dK|/max|K| <= 1e-12 and per entry
+                      |dK_ij| <= 1e-12 * max(|K_ij|, 1e-6 max|K|);
+  log-likelihood:     |d|/|ll| <= 1e-9;  -inf must agree exactly.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import assert_matrix_parity, rel_err
+from oracle import gp_oracle as go
+
+pytestmark = pytest.mark.gpu
+
+LL_RTOL = 1e-9
+PAIRS = {"rv": ("rv", "rverr"), "bis": ("bis", "sig_bis"), "rhk": ("rhk", "sig_rhk")}
+
+
+@pytest.fixture(scope="module")
+def mf():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import miniframe_b200
+    from miniframe_b200 import _lib
+    _lib.load()
+    return miniframe_b200
+
+
+def _means(mf, names):
+    table = {None: None, "Constant": mf.means.Constant, "Linear": mf.means.Linear,
+             "Parabola": mf.means.Parabola, "Cubic": mf.means.Cubic, "Sine": mf.means.Sine,
+             "Keplerian": mf.means.Keplerian}
+    return [table[m] for m in names]
+
+
+def _make_gp(mf, golden, case):
+    d = golden.data(case["data"])
+    kern = getattr(mf.kernels, case["kernel"])
+    if case["framework"] == "SMALLgp":
+        args = []
+        for o in case["order"]:
+            args += [d[PAIRS[o][0]], d[PAIRS[o][1]]]
+        ek = None if case["extrakernel"] is None else getattr(mf.kernels, case["extrakernel"])
+        return mf.SMALLgp.SMALLgp(kern, ek, _means(mf, case["means"]), d["t"], *args)
+    cls = mf.BIGgp.BIGgp if case["framework"] == "BIGgp" else mf.BIGgpPlusJitt.BIGgp
+    return cls(kern, _means(mf, case["means"]), t=d["t"], rv=d["rv"], rverr=d["rverr"],
+               rhk=d["rhk"], sig_rhk=d["sig_rhk"], bis=d["bis"], sig_bis=d["sig_bis"])
+
+
+def _loglike(gp, case):
+    if case["framework"] == "SMALLgp":
+        return gp.log_likelihood(case["a"], case["b"], case["c"])
+    if case["framework"] == "BIGgpPlusJitt":
+        return gp.log_likelihood(case["a"], case["b"], case["jitter"])
+    return gp.log_likelihood(case["a"], case["b"])
+
+
+def _matrix(gp, case):
+    if case["framework"] == "SMALLgp":
+        return gp.compute_matrix(case["a"], case["c"])
+    kw = dict(case.get("matrix_kwargs") or {})
+    if case["framework"] == "BIGgpPlusJitt":
+        return gp.compute_matrix(case["a"], case["jitter"], **kw)
+    return gp.compute_matrix(case["a"], **kw)
+
+
+def test_golden_covariance_matrices(mf, golden):
+    n = 0
+    for case in golden.meta["cases"]:
+        Kref = golden.K(case)
+        if Kref is None:
+            continue
+        K = _matrix(_make_gp(mf, golden, case), case)
+        assert K.shape == Kref.shape and K.dtype == np.float64
+        assert_matrix_parity(K, Kref)
+        n += 1
+    assert n >= 15
+
+
+def test_golden_log_likelihoods(mf, golden):
+    worst = 0.0
+    for case in golden.meta["cases"]:
+        ll = _loglike(_make_gp(mf, golden, case), case)
+        assert isinstance(ll, float)
+        err = rel_err(ll, case["ll"])
+        assert err <= LL_RTOL, (case["name"], ll, case["ll"])
+        worst = max(worst, err)
+    print("worst relative log-likelihood error over golden cases: %.3e" % worst)
+
+
+def test_reference_quirks_survive(mf, golden):
+    # Q3: BIGgp.log_likelihood ignores nugget; compute_matrix honours it
+    case = golden.cases["big_qp2_40"]
+    gp = _make_gp(mf, golden, case)
+    assert gp.log_likelihood(case["a"], [], nugget=True) == gp.log_likelihood(case["a"], [], nugget=False)
+    assert gp.minus_log_likelihood(case["a"], []) == -gp.log_likelihood(case["a"], [])
+    # non positive definite -> -inf, not an exception
+    nonpd = golden.cases["big_nonpd"]
+    assert _loglike(_make_gp(mf, golden, nonpd), nonpd) == -np.inf
+    # NaN hyper-parameters raise like scipy's check_finite does in the reference
+    with pytest.raises(ValueError):
+        gp.log_likelihood([np.nan] + case["a"][1:], [])
+    # mean parameters: wrong length asserts, right length mutates state
+    gm = _make_gp(mf, golden, golden.cases["big_means"])
+    with pytest.raises(AssertionError):
+        gm.log_likelihood(golden.cases["big_means"]["a"], [0.0])
+    gm.log_likelihood(golden.cases["big_means"]["a"], golden.cases["big_means"]["b"])
+    assert gm.mean_pars == golden.cases["big_means"]["b"]
+    # PlusJitt.minus_log_likelihood is unusable without c, as in the reference
+    gj = _make_gp(mf, golden, golden.cases["jitt_qp2_40"])
+    with pytest.raises(TypeError):
+        gj.minus_log_likelihood(golden.cases["jitt_qp2_40"]["a"], [])
+
+
+def test_block_methods(mf, golden):
+    case = golden.cases["big_qp2_40"]
+    d = golden.data(case["data"])
+    gp = _make_gp(mf, golden, case)
+    k11, k22, k33, k12, k13, k23 = go.biggp_blocks_literal(case["kernel"], case["a"], d["t"])
+    for got, want in ((gp.k11(case["a"], d["t"]), k11), (gp.k22(case["a"], d["t"]), k22),
+                      (gp.k33(case["a"], d["t"]), k33), (gp.k12(case["a"], d["t"]), k12),
+                      (gp.k13(case["a"], d["t"]), k13), (gp.k23(case["a"], d["t"]), k23)):
+        assert_matrix_parity(got, want)
+
+
+@pytest.mark.parametrize("N", [1, 2, 5, 21, 22, 33, 43, 64, 85, 128, 150])
+def test_edge_sizes_against_oracle(mf, N):
+    """n = 3N walks over every tile boundary of the kernels: below one 64 block,
+    exact multiples of 64 and 128 (the residual row then opens a new tile), odd N
+    (scalar store path), ragged last blocks."""
+    t, (rv, rhk, bis), (e1, e2, e3) = go.synthetic_series(N, seed=N)
+    H = go.synthetic_biggp_hypers(5, seed=N)
+    gp = mf.BIGgp.BIGgp(mf.kernels.QuasiPeriodic, [None, None, None], t, rv, e1, rhk, e2, bis, e3)
+    y = go.biggp_y(rv, rhk, bis)
+    got = gp.log_likelihood_batch(H)
+    assert got.shape == (5,) and got.dtype == np.float64
+    for i in range(5):
+        want = go.biggp_loglike_literal("QuasiPeriodic", H[i], t, y, e1, e2, e3)
+        assert rel_err(got[i], want) <= LL_RTOL, (N, i, got[i], want)
+    K = gp.compute_matrix(H[0])
+    assert_matrix_parity(K, go.biggp_matrix_literal("QuasiPeriodic", H[0], t, e1, e2, e3))
+    assert np.array_equal(K, K.T)
+
+
+def test_factor_and_z_against_lapack(mf):
+    """The factor itself: L L^T = K, L matches numpy's Cholesky, z = L^-1 r."""
+    import torch
+    from miniframe_b200._engine import Engine
+    eng = Engine.get()
+    N = 70
+    t, (rv, rhk, bis), (e1, e2, e3) = go.synthetic_series(N, seed=11)
+    H = go.synthetic_biggp_hypers(3, seed=11)
+    gp = mf.BIGgp.BIGgp(mf.kernels.QuasiPeriodic, [None, None, None], t, rv, e1, rhk, e2, bis, e3)
+    n = 3 * N
+    prob = gp._problem(N)
+    Kd = eng.build_cov(prob, eng.tensor(t), eng.tensor(gp._diag_yerr()), eng.tensor(H), None, full=False)
+    resid = eng.tensor(go.biggp_y(rv, rhk, bis)[None, :])
+    ll, info = eng.potrf_loglike(Kd, n, resid)
+    assert info.cpu().numpy().tolist() == [0, 0, 0]
+    out = Kd.cpu().numpy()
+    for b in range(3):
+        Kref = go.biggp_matrix_literal("QuasiPeriodic", H[b], t, e1, e2, e3)
+        Lref = np.linalg.cholesky(Kref)
+        L = np.tril(out[b, :n, :n])
+        assert np.abs(L - Lref).max() <= 1e-10 * np.abs(Lref).max()
+        assert np.abs(L @ L.T - Kref).max() <= 1e-13 * np.abs(Kref).max()
+        zref = np.linalg.solve(Lref, go.biggp_y(rv, rhk, bis))
+        assert np.abs(out[b, n, :n] - zref).max() <= 1e-9 * np.abs(zref).max()
+    # stand-alone solve + logdet on that factor, a different residual per sample
+    rng = np.random.default_rng(3)
+    R = rng.standard_normal((3, n))
+    z, ll2 = eng.solve_logdet(Kd, n, eng.tensor(R), info)
+    for b in range(3):
+        Kref = go.biggp_matrix_literal("QuasiPeriodic", H[b], t, e1, e2, e3)
+        assert rel_err(float(ll2[b]), go.loglike_from_matrix(Kref, R[b])) <= LL_RTOL
+
+
+def test_batch_mixes_failures_and_successes(mf, golden):
+    d = golden.data("spot40_noerr")
+    gp = mf.BIGgp.BIGgp(mf.kernels.SquaredExponential, [None, None, None], t=d["t"], rv=d["rv"],
+                        rverr=d["rverr"], rhk=d["rhk"], sig_rhk=d["sig_rhk"], bis=d["bis"],
+                        sig_bis=d["sig_bis"])
+    bad = [500.0, 0.0, 1.0, 0.5, 0.8, 0.9, 0.4]          # golden big_nonpd
+    good = [3.0, 0.5, 1.0, 0.5, 0.8, 0.9, 0.4]
+    A = np.array([good, bad, good, bad, bad, good])
+    y = go.biggp_y(d["rv"], d["rhk"], d["bis"])
+    got = gp.log_likelihood_batch(A)
+    want = np.array([go.biggp_loglike_literal("SquaredExponential", a, d["t"], y, d["rverr"],
+                                              d["sig_rhk"], d["sig_bis"]) for a in A])
+    assert np.array_equal(np.isinf(got), np.isinf(want)) and np.isinf(want).sum() == 3
+    ok = ~np.isinf(want)
+    assert np.all(np.abs(got[ok] - want[ok]) <= LL_RTOL * np.abs(want[ok]))
+
+
+def test_plusjitt_and_smallgp_batches(mf, golden):
+    d = golden.data("synth64")
+    y = go.biggp_y(d["rv"], d["rhk"], d["bis"])
+    H, J = go.synthetic_biggp_hypers(7, seed=4), go.synthetic_jitter(7, seed=4)
+    gj = mf.BIGgpPlusJitt.BIGgp(mf.kernels.QuasiPeriodic, [None, None, None], t=d["t"], rv=d["rv"],
+                                rverr=d["rverr"], rhk=d["rhk"], sig_rhk=d["sig_rhk"], bis=d["bis"],
+                                sig_bis=d["sig_bis"])
+    got = gj.log_likelihood_batch(H, None, J)
+    for i in range(7):
+        want = go.biggp_loglike_literal("QuasiPeriodic", H[i], d["t"], y, d["rverr"], d["sig_rhk"],
+                                        d["sig_bis"], jitter=J[i])
+        assert rel_err(got[i], want) <= LL_RTOL
+    # SMALLgp, M = 3 with an extra kernel, per-sample mean parameters
+    gs = mf.SMALLgp.SMALLgp(mf.kernels.QuasiPeriodic, mf.kernels.SquaredExponential,
+                            [mf.means.Constant, None, mf.means.Linear], d["t"],
+                            d["rv"], d["rverr"], d["bis"], d["sig_bis"], d["rhk"], d["sig_rhk"])
+    rng = np.random.default_rng(9)
+    B = 6
+    A = np.column_stack([rng.uniform(10, 40, B), rng.uniform(0.8, 1.6, B), rng.uniform(15, 35, B),
+                         rng.uniform(0.01, 0.1, B)] +
+                        [rng.uniform(0.2, 1.5, B), rng.uniform(0.0, 0.3, B), rng.uniform(0.0, 0.01, B)] * 3)
+    C = np.column_stack([rng.uniform(2, 6, B), rng.uniform(0.01, 0.05, B)] + [rng.uniform(0.1, 0.6, B)] * 3)
+    Bm = rng.normal(0, 0.2, (B, 3))
+    got = gs.log_likelihood_batch(A, Bm, C)
+    yerr2 = np.concatenate([d["rverr"], d["sig_bis"], d["sig_rhk"]]) ** 2
+    ycat = np.concatenate([d["rv"], d["bis"], d["rhk"]])
+    for i in range(B):
+        gs.mean_pars = Bm[i]
+        want = go.smallgp_loglike_literal("QuasiPeriodic", "SquaredExponential", A[i], C[i], d["t"],
+                                          ycat - gs.mean(), yerr2, 3)
+        assert rel_err(got[i], want) <= LL_RTOL, (i, got[i], want)
+
+
+def test_full_size_n1500_against_oracle(mf):
+    """BASELINE config 3 shape (N = 500, n = 1500), a handful of samples the CPU
+    oracle can finish in seconds: covariance entries and log-likelihoods."""
+    N = 500
+    t, (rv, rhk, bis), (e1, e2, e3) = go.synthetic_series(N, seed=0)
+    H = go.synthetic_biggp_hypers(4, seed=0)
+    gp = mf.BIGgp.BIGgp(mf.kernels.QuasiPeriodic, [None, None, None], t, rv, e1, rhk, e2, bis, e3)
+    y = go.biggp_y(rv, rhk, bis)
+    got = gp.log_likelihood_batch(H)
+    conds = []
+    for i in range(4):
+        Kref = go.biggp_matrix_literal("QuasiPeriodic", H[i], t, e1, e2, e3)
+        want = go.loglike_from_matrix(Kref, y)
+        assert rel_err(got[i], want) <= LL_RTOL, (i, got[i], want)
+        if i == 0:
+            assert_matrix_parity(gp.compute_matrix(H[0]), Kref)
+            conds.append(np.linalg.cond(Kref))
+    print("n=1500 parity ok; cond(K[0]) = %.3e" % conds[0])
+
+
+def test_full_size_properties(mf):
+    """Size-independent checks at the benchmark shape with more samples than
+    resident CTAs (2 x 148): bit-reproducibility, independence from the batch slot,
+    and the exact scaling law  ll(s K, s r) = ll(K, r) - n log s."""
+    import torch
+    N, B = 500, 320
+    t, (rv, rhk, bis), (e1, e2, e3) = go.synthetic_series(N, seed=1)
+    H = go.synthetic_biggp_hypers(8, seed=1)
+    A = np.tile(H, (B // 8, 1))
+    gp = mf.BIGgp.BIGgp(mf.kernels.QuasiPeriodic, [None, None, None], t, rv, e1, rhk, e2, bis, e3)
+    one = gp.log_likelihood_batch(A)
+    two = gp.log_likelihood_batch(A)
+    assert np.array_equal(one, two)
+    assert np.array_equal(one.reshape(-1, 8), np.tile(one[:8], (B // 8, 1)))
+    assert np.all(np.isfinite(one))
+    s = 4.0                                  # power of two: every product scales exactly
+    gp2 = mf.BIGgp.BIGgp(mf.kernels.QuasiPeriodic, [None, None, None], t, s * rv, s * e1, s * rhk,
+                         s * e2, s * bis, s * e3)
+    Hs = H.copy()
+    Hs[:, 4:] *= s
+    scaled = gp2.log_likelihood_batch(Hs)
+    n = 3 * N
+    assert np.all(np.abs(scaled - (one[:8] - n * np.log(s))) <= 1e-11 * np.abs(one[:8]))
+    # torch in -> device tensor out, same numbers
+    dev = gp.log_likelihood_batch(torch.as_tensor(H, device="cuda"))
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), one[:8])
+
+
+def test_chunked_workspace_gives_identical_results(mf):
+    from miniframe_b200._engine import Engine
+    eng = Engine.get()
+    N = 40
+    t, (rv, rhk, bis), (e1, e2, e3) = go.synthetic_series(N, seed=2)
+    H = go.synthetic_biggp_hypers(23, seed=2)
+    gp = mf.BIGgp.BIGgp(mf.kernels.QuasiPeriodic, [None, None, None], t, rv, e1, rhk, e2, bis, e3)
+    whole = gp.log_likelihood_batch(H)
+    eng.max_workspace_bytes = 5 * eng.matrix_stride(3 * N) * 8      # 5 matrices per chunk
+    eng._ws = None
+    try:
+        chunked = gp.log_likelihood_batch(H)
+    finally:
+        eng.max_workspace_bytes = None
+        eng._ws = None
+    assert np.array_equal(whole, chunked)
+
+
+def test_abi_argument_errors(mf):
+    from miniframe_b200 import _lib
+    from miniframe_b200._engine import Engine
+    eng = Engine.get()
+    prob = _lib.Problem(framework=7, kernel=1, extra_kernel=-1, n_series=3, n_epochs=4,
+                        hyper_len=9, extra_len=0, reserved=0, nugget=0.0)
+    import torch
+    buf = torch.zeros(4096, dtype=torch.float64, device="cuda")
+    st = eng.lib.mf_build_cov(eng.handle, ctypes.byref(prob), 1, eng.ptr(buf), eng.ptr(buf), eng.ptr(buf),
+                              None, 1, eng.ptr(buf), 16, 13 * 16, eng.stream())
+    assert st == 1 and b"framework" in eng.lib.mf_last_error(eng.handle)
+    st = eng.lib.mf_potrf_loglike(eng.handle, 1, 12, eng.ptr(buf), 12, 13 * 12, None, 0, eng.ptr(buf),
+                                  eng.ptr(buf), eng.stream())
+    assert st == 1

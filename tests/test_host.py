@@ -1,0 +1,168 @@
+"""CPU: host-side logic of the drop-in package (kernel/mean classes, parameter
+bookkeeping, residuals) against the golden vectors and the oracle, and the C-ABI
+library: it must load and export every symbol include/miniframe_b200.h declares.
+No compute entry point is called here (no GPU)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import gp_oracle as go
+from oracle import ref_shim
+
+import miniframe_b200
+from miniframe_b200 import _lib, kernels, means
+from miniframe_b200.BIGgp import BIGgp
+from miniframe_b200.BIGgpPlusJitt import BIGgp as BIGgpJ
+from miniframe_b200.SMALLgp import SMALLgp
+
+MEANS = {None: None, "Constant": means.Constant, "Linear": means.Linear, "Parabola": means.Parabola,
+         "Cubic": means.Cubic, "Sine": means.Sine, "Keplerian": means.Keplerian}
+PAIRS = {"rv": ("rv", "rverr"), "bis": ("bis", "sig_bis"), "rhk": ("rhk", "sig_rhk")}
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "miniframe_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(mf_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()                       # raises if the .so is missing or a symbol is not exported
+    assert lib.mf_version() == 100
+    assert lib.mf_status_string(0) == b"ok"
+    # layout helpers are host arithmetic
+    assert lib.mf_ld(1500) == 1504 and lib.mf_ld(1504) == 1504 and lib.mf_ld(1) == 16
+    assert lib.mf_matrix_stride(1500) == 1501 * 1504
+    assert lib.mf_workspace_bytes(4, 600) == 4 * 601 * 608 * 8
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    t, (rv, rhk, bis), (e1, e2, e3) = go.synthetic_series(16, seed=0)
+    gp = BIGgp(kernels.QuasiPeriodic, [None, None, None], t, rv, e1, rhk, e2, bis, e3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gp.log_likelihood(go.synthetic_biggp_hypers(1)[0], [])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gp.compute_matrix(go.synthetic_biggp_hypers(1)[0])
+
+
+def test_subclass_order_and_names():
+    for base, names in ((kernels.QuasiPeriodic, ["dQP_dt1", "dQP_dt2", "ddQP_dt2dt1", "dddQP_dt2ddt1",
+                                                 "dddQP_ddt2dt1", "ddddQP_ddt2ddt1"]),
+                        (kernels.SquaredExponential, ["dSE_dt1", "dSE_dt2", "ddSE_dt2dt1", "dddSE_dt2ddt1",
+                                                      "dddSE_ddt2dt1", "ddddSE_ddt2ddt1"])):
+        assert [c.__name__ for c in base.__subclasses__()] == names
+    assert miniframe_b200.BIGgp.BIGgp is BIGgp and miniframe_b200.SMALLgp.SMALLgp is SMALLgp
+
+
+def test_kernel_classes_match_oracle():
+    rng = np.random.default_rng(5)
+    t = np.sort(rng.uniform(0, 60, 37))
+    r = t[:, None] - t[None, :]
+    qp, se = (17.0, 1.3, 23.0, 0.07), (9.0, 0.05)
+    order = ["k", "dt1", "dt2", "dt2dt1", "dt2ddt1", "ddt2dt1", "ddt2ddt1"]
+    for base, pars, fam in ((kernels.QuasiPeriodic, qp, "QuasiPeriodic"),
+                            (kernels.SquaredExponential, se, "SquaredExponential")):
+        classes = [base] + base.__subclasses__()
+        for cls, which in zip(classes, order):
+            ref = go.FAMILY[fam][which]
+            got = cls(*pars)(r)
+            want = ref(r, *pars)
+            scale = np.abs(want).max()
+            assert np.abs(got - want).max() <= 1e-12 * scale, (cls.__name__,)
+            # white-noise quirk Q1: square r gets wn^2 on the diagonal, a row of lags does not
+            assert np.allclose(np.diag(got), np.diag(want))
+            row = r[3:4, :]            # (1, n): numpy broadcasts the 1x1 "identity" -> wn^2 everywhere
+            assert np.allclose(cls(*pars)(row), ref(row, *pars) if False else cls(*pars)._value(row) + pars[-1] ** 2)
+            rect = r[2:9, :]           # (7, n): cannot broadcast -> bare function
+            assert np.allclose(cls(*pars)(rect), cls(*pars)._value(rect))
+    k = kernels.QuasiPeriodic(*qp) + 2.0
+    assert np.allclose(k(r), kernels.QuasiPeriodic(*qp)(r) + 2.0)
+    k = 3.0 * kernels.SquaredExponential(*se)
+    assert np.allclose(k(r), 3.0 * kernels.SquaredExponential(*se)(r))
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+def test_kernel_and_mean_classes_match_live_reference():
+    ref = ref_shim.load()
+    rng = np.random.default_rng(6)
+    t = np.sort(rng.uniform(0, 60, 29))
+    r = t[:, None] - t[None, :]
+    for name, pars in (("QuasiPeriodic", (17.0, 1.3, 23.0, 0.07)), ("SquaredExponential", (9.0, 0.05))):
+        mine = [getattr(kernels, name)] + getattr(kernels, name).__subclasses__()
+        theirs = [getattr(ref.kernels, name)] + getattr(ref.kernels, name).__subclasses__()
+        for a, b in zip(mine, theirs):
+            assert a.__name__ == b.__name__
+            for lag in (r, r[0], r[2:5, :], r[1:2, :]):
+                got, want = a(*pars)(lag), b(*pars)(lag)
+                assert np.abs(got - want).max() <= 2e-12 * max(np.abs(want).max(), 1e-300), a.__name__
+    pars = {"Constant": (0.7,), "Linear": (0.02, -0.4), "Parabola": (1e-3, 0.02, 0.3),
+            "Cubic": (1e-5, 1e-3, 0.02, 0.3), "Sine": (0.8, 13.0, 0.4, 0.1),
+            "oldKeplerian": (11.0, 2.0, 0.3, 0.7, 1.5), "Keplerian": (11.0, 2.0, 0.3, 0.7, 1.5, 0.2),
+            "TOI175keplerians": (3.7, 1.0, 0.1, 0.2, 0.3, 7.4, 2.0, 0.2, 0.4, 0.5, 25.6, 1.5, 0.05, 1.0, 2.0, 0.3)}
+    for name, p in pars.items():
+        a, b = getattr(means, name)(*p), getattr(ref.means, name)(*p)
+        assert a._parsize == b._parsize == len(p)
+        assert np.array_equal(a(t), b(t)), name
+        assert getattr(means, name).initialize().pars == [0.] * len(p)
+
+
+def test_residuals_and_mean_protocol_match_golden(golden):
+    n = 0
+    for case in golden.meta["cases"]:
+        d = golden.data(case["data"])
+        ms = [MEANS[m] for m in case["means"]]
+        if case["framework"] == "SMALLgp":
+            args = []
+            for o in case["order"]:
+                args += [d[PAIRS[o][0]], d[PAIRS[o][1]]]
+            ek = None if case["extrakernel"] is None else getattr(kernels, case["extrakernel"])
+            gp = SMALLgp(getattr(kernels, case["kernel"]), ek, ms, d["t"], *args)
+        else:
+            cls = BIGgp if case["framework"] == "BIGgp" else BIGgpJ
+            gp = cls(getattr(kernels, case["kernel"]), ms, t=d["t"], rv=d["rv"], rverr=d["rverr"],
+                     rhk=d["rhk"], sig_rhk=d["sig_rhk"], bis=d["bis"], sig_bis=d["sig_bis"])
+        assert gp.mean_pars_size == len(case["b"])
+        resid = gp._residual_rows(np.asarray(case["b"])[None, :] if case["b"] else None, 1)
+        assert np.array_equal(resid[0], golden.resid(case)), case["name"]
+        n += 1
+    assert n >= 30
+
+
+def test_biggp_constructor_attributes():
+    t, (rv, rhk, bis), (e1, e2, e3) = go.synthetic_series(12, seed=1)
+    gp = BIGgp(kernels.QuasiPeriodic, [means.Constant, None, means.Linear], t=t, rv=rv, rverr=e1,
+               rhk=rhk, sig_rhk=e2, bis=bis, sig_bis=e3)
+    assert np.array_equal(gp.y, np.concatenate([rv, bis, rhk]))            # quirk Q2
+    assert np.array_equal(gp.yerr, np.concatenate([e1, e3, e2]))
+    assert gp.tt.shape == (36,) and gp.tplot.shape == (36,)
+    assert gp.mean_pars_size == 3 and gp.mean_pars == [0., 0., 0.]
+    gp.mean_pars = [1.0, 2.0, 3.0]
+    assert gp.means[0].pars == [1.0] and gp.means[2].pars == [2.0, 3.0]
+    with pytest.raises(AssertionError):
+        gp.mean_pars = [1.0]
+    assert gp._kernel_pars(np.arange(9.0)) == [0.0, 1.0, 2.0, 3.0]
+    assert list(gp._scaling_pars(np.arange(9.0))) == [4.0, 5.0, 6.0, 7.0, 8.0]
+    with pytest.raises(ValueError):
+        gp._kernel_pars(np.arange(8.0))
+    assert gp.dKdt1 is kernels.dQP_dt1 and gp.ddddKddt2ddt1 is kernels.ddddQP_ddt2ddt1
+    # diag order follows the covariance blocks [rv, rhk, bis]
+    assert np.array_equal(gp._diag_yerr(), np.concatenate([e1 ** 2, e2 ** 2, e3 ** 2]))
+
+
+def test_smallgp_constructor_and_packing():
+    t, (y1, y2, y3), (e1, e2, e3) = go.synthetic_series(10, seed=2)
+    gp = SMALLgp(kernels.QuasiPeriodic, kernels.SquaredExponential, [None, None, None], t,
+                 y1, e1, y2, e2, y3, e3)
+    assert gp.number_models == 3 and np.array_equal(gp.yerr, np.concatenate([e1, e2, e3]) ** 2)
+    a = np.arange(13.0)
+    assert list(gp._scaling_pars(a, 1)) == [4.0, 5.0, 6.0] and list(gp._scaling_pars(a, 3)) == [10.0, 11.0, 12.0]
+    prob = gp._problem(10)
+    assert (prob.hyper_len, prob.extra_len, prob.nugget) == (13, 5, 0.01)
+    hyper, extra = gp._pack(prob, a[None, :], np.array([[3.0, 0.1, 0.5, 0.6, 0.7]]))
+    assert np.array_equal(hyper[0], a) and np.array_equal(extra[0], [3.0, 0.1, 0.5, 0.6, 0.7])
+    with pytest.raises(AssertionError):
+        SMALLgp(kernels.QuasiPeriodic, None, [None, None], t, y1, e1, y2, e2, y3, e3)
