@@ -37,8 +37,11 @@ struct SampleCoefs {
     BlockCoef c[MF_MAX_SERIES][MF_MAX_SERIES];   // [row block][col block]
 };
 
+// E, Gdd, G4 are even in the lag and AE is odd.  H is odd for the SE family but NOT
+// for the quasi-periodic one: the reference builds it from sin*sin (quirk Q4,
+// kernels.py:449), so H(-r) != -H(r) and both are kept: Hf = H(r), Hr = H(-r).
 struct Bases {
-    double E, AE, Gdd, H, G4;
+    double E, AE, Gdd, Hf, Hr, G4;
 };
 
 __device__ inline void mf_kern_const(int kernel, const double* p, KernConst& o) {
@@ -68,75 +71,106 @@ __device__ inline void mf_kern_const(int kernel, const double* p, KernConst& o) 
     }
 }
 
+// Explicitly rounded FP64 operations: the compiler neither fuses nor splits these,
+// so every inlined instance of the covariance algebra performs the same IEEE
+// operations and K(i, j) == K(j, i) bit for bit whichever thread/slot computed it.
+__device__ __forceinline__ double dm(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double da(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double df(double a, double b, double c) { return __fma_rn(a, b, c); }
+
+#define MF_4PI   (4.0 * MF_PI)
+#define MF_4PI2  (4.0 * MF_PI * MF_PI)
+#define MF_16PI3 (16.0 * MF_PI * MF_PI * MF_PI)
+#define MF_64PI3 (64.0 * MF_PI * MF_PI * MF_PI)
+#define MF_16PI4 (16.0 * MF_PI * MF_PI * MF_PI * MF_PI)
+
 // Base functions at lag r = t_i - t_j, white noise NOT included.
+// Everything is evaluated at |r| and the parity of each function applied
+// afterwards, so K(i, j) and K(j, i) come out of identical arithmetic and the
+// matrix is symmetric to the last bit (the reference's is: its lower blocks are
+// transposes, BIGgp.py:270-271, SMALLgp.py:241).
 // The sin/cos argument is formed exactly as the reference forms it,
 // x = (pi * r) / P with a true division (kernels.py:295): E is sensitive to the
 // last bit of x (dE/E ~ 4 s/ell_p^2 dx), everything else tolerates a few ulp.
 template <int KERNEL, bool HIGH>
-__device__ __forceinline__ void mf_bases(double r, const KernConst& k, Bases& o) {
+__device__ __forceinline__ void mf_bases(double r_signed, const KernConst& k, Bases& o) {
+    const bool neg = r_signed < 0.0;
+    const double r = fabs(r_signed);
+    double AEa, Hp = 0.0, Hm = 0.0;
     if (KERNEL == MF_KERNEL_QP) {
-        double x = (MF_PI * r) / k.P;
+        const double x = __ddiv_rn(dm(MF_PI, r), k.P);
         double s, c;
         sincos(x, &s, &c);
-        double ss = s * s, cc = c * c, sc = s * c;
-        double rr3 = r * k.i_f3;                        // r / f3
+        const double ss = dm(s, s), cc = dm(c, c), sc = dm(s, c);
+        const double rr3 = dm(r, k.i_f3);                         // r / f3
         // kernels.py:297  exp(-(2 s s / f2) - 0.5 r r / f3)
-        double E = exp(-(2.0 * ss) * k.i_f2 - 0.5 * r * rr3);
+        const double E = exp(df(dm(-0.5, r), rr3, -dm(dm(2.0, ss), k.i_f2)));
         // kernels.py:365  A = 4 pi s c / (f2 P) + r / f3 ; dK/dt2 = A E, dK/dt1 = -A E
-        double A = (4.0 * MF_PI) * sc * k.i_f2P + rr3;
+        const double A = df(dm(MF_4PI, sc), k.i_f2P, rr3);
         // kernels.py:400-405  q0 = 1/f3 + 4 pi^2 (c^2 - s^2) / (f2 P^2)
-        double q0 = k.i_f3 + (4.0 * MF_PI * MF_PI) * cc * k.i_f2P2 - (4.0 * MF_PI * MF_PI) * ss * k.i_f2P2;
+        const double q0 = df(-dm(MF_4PI2, ss), k.i_f2P2, df(dm(MF_4PI2, cc), k.i_f2P2, k.i_f3));
         o.E = E;
-        o.AE = A * E;
-        o.Gdd = (q0 - A * A) * E;
+        AEa = dm(A, E);
+        o.Gdd = dm(df(-A, A, q0), E);
         if (HIGH) {
-            // kernels.py:448-456 (third derivative; j2 uses sin*sin as the
-            // reference does - quirk Q4) and kernels.py:573-587 (fourth)
-            double j2 = rr3 + (4.0 * MF_PI) * ss * k.i_f2P;
-            double j8 = (16.0 * MF_PI * MF_PI * MF_PI) * sc * k.i_f2P3;
-            o.H = (j2 * j2 * j2 - 3.0 * q0 * j2 - j8) * E;
-            double A2 = A * A;
-            double p4 = A2 * A2 - 6.0 * q0 * A2 + 3.0 * q0 * q0
-                        - (64.0 * MF_PI * MF_PI * MF_PI) * sc * A * k.i_f2P3
-                        - (16.0 * MF_PI * MF_PI * MF_PI * MF_PI) * ss * k.i_f2P4
-                        + (16.0 * MF_PI * MF_PI * MF_PI * MF_PI) * cc * k.i_f2P4;
-            o.G4 = p4 * E;
+            // kernels.py:448-456: (j1 j2 + j3 j4 + 2 j5 j6 - j8) = j2^3 - 3 q0 j2 - j8 with
+            // j2 = r/f3 + 4 pi s s/(f2 P)  (sin*sin as shipped) and j8 = 16 pi^3 c s/(f2 P^3)
+            const double j2e = dm(dm(MF_4PI, ss), k.i_f2P);      // even part of j2
+            const double j8 = dm(dm(MF_16PI3, sc), k.i_f2P3);
+            const double j2p = da(j2e, rr3), j2m = da(j2e, -rr3);
+            const double q3 = dm(3.0, q0);
+            Hp = dm(df(j2p, dm(j2p, j2p), -df(q3, j2p, j8)), E);   // at +|r|
+            Hm = dm(df(j2m, dm(j2m, j2m), -df(q3, j2m, -j8)), E);  // at -|r|
+            // kernels.py:573-587: A^4 - 6 q0 A^2 + 3 q0^2 - 64 pi^3 c s A/(f2 P^3)
+            //                     - 16 pi^4 s^2/(f2 P^4) + 16 pi^4 c^2/(f2 P^4)
+            const double A2 = dm(A, A);
+            double p4 = df(A2, A2, dm(q3, q0));
+            p4 = df(-dm(6.0, q0), A2, p4);
+            p4 = df(-dm(dm(MF_64PI3, sc), A), k.i_f2P3, p4);
+            p4 = df(-dm(MF_16PI4, ss), k.i_f2P4, p4);
+            p4 = df(dm(MF_16PI4, cc), k.i_f2P4, p4);
+            o.G4 = dm(p4, E);
         } else {
-            o.H = 0.0;
             o.G4 = 0.0;
         }
     } else {
         // kernels.py:96-259
-        double r2 = r * r;
-        double E = exp(-0.5 * r2 * k.i_f2);
+        const double r2 = dm(r, r);
+        const double E = exp(dm(dm(-0.5, r2), k.i_f2));
         o.E = E;
-        o.AE = r * k.i_f2 * E;                          // dK/dt2 (kernels.py:143)
-        o.Gdd = (k.i_f2 - r2 * k.i_l4) * E;             // kernels.py:165
+        AEa = dm(dm(r, k.i_f2), E);                             // dK/dt2 (kernels.py:143)
+        o.Gdd = dm(df(-r2, k.i_l4, k.i_f2), E);                 // kernels.py:165
         if (HIGH) {
-            o.H = (r2 * r * k.i_l6 - 3.0 * r * k.i_l4) * E;                   // kernels.py:191
-            o.G4 = (r2 * r2 * k.i_l8 - 6.0 * r2 * k.i_l6 + 3.0 * k.i_l4) * E; // kernels.py:251
+            Hp = dm(df(dm(r2, r), k.i_l6, -dm(dm(3.0, r), k.i_l4)), E);         // kernels.py:191
+            Hm = -Hp;
+            double p4 = df(dm(r2, r2), k.i_l8, dm(3.0, k.i_l4));                // kernels.py:251
+            p4 = df(-dm(6.0, r2), k.i_l6, p4);
+            o.G4 = dm(p4, E);
         } else {
-            o.H = 0.0;
             o.G4 = 0.0;
         }
     }
+    o.AE = neg ? -AEa : AEa;
+    o.Hf = neg ? Hm : Hp;
+    o.Hr = neg ? Hp : Hm;
 }
 
 // plain K(r) of a kernel family selected at run time (extra kernel Z(t))
-__device__ __forceinline__ double mf_kernel_value(int kernel, double r, const KernConst& k) {
+__device__ __forceinline__ double mf_kernel_value(int kernel, double r_signed, const KernConst& k) {
+    const double r = fabs(r_signed);
     if (kernel == MF_KERNEL_QP) {
-        double s = sin((MF_PI * r) / k.P);
-        return exp(-(2.0 * s * s) * k.i_f2 - 0.5 * r * r * k.i_f3);
+        const double s = sin(__ddiv_rn(dm(MF_PI, r), k.P));
+        return exp(df(dm(-0.5, r), dm(r, k.i_f3), -dm(dm(2.0, dm(s, s)), k.i_f2)));
     }
-    return exp(-0.5 * r * r * k.i_f2);
+    return exp(dm(dm(-0.5, dm(r, r)), k.i_f2));
 }
 
 __device__ inline void mf_set_pair(SampleCoefs& sc, int p, int q, double cE, double cAE,
                                    double cGdd, double cH, double cG4, double cW) {
     BlockCoef u = {cE, cAE, cGdd, cH, cG4, cW};
     sc.c[p][q] = u;
-    if (p != q) {   // lower block (q, p) is the transpose: odd functions change sign
-        BlockCoef l = {cE, -cAE, cGdd, -cH, cG4, cW};
+    if (p != q) {   // lower block (q, p) is the transpose: AE changes sign, H is read at -r
+        BlockCoef l = {cE, -cAE, cGdd, cH, cG4, cW};
         sc.c[q][p] = l;
     }
 }
@@ -202,15 +236,19 @@ __device__ __forceinline__ double mf_entry(const SampleCoefs& sc, const Bases& b
                                            bool same_epoch, double ez, double diag_add,
                                            double nugget) {
     const BlockCoef& c = sc.c[P][Q];
-    double v = c.cE * b.E + c.cGdd * b.Gdd + c.cG4 * b.G4 + c.cAE * b.AE + c.cH * b.H;
-    if (same_epoch) v += c.cW * sc.k.wn2;
+    double v = dm(c.cE, b.E);
+    v = df(c.cGdd, b.Gdd, v);
+    v = df(c.cG4, b.G4, v);
+    v = df(c.cAE, b.AE, v);
+    v = df(c.cH, (P > Q ? b.Hr : b.Hf), v);
+    if (same_epoch) v = df(c.cW, sc.k.wn2, v);
     if (P == Q) {
-        if (sc.amp2[P] != 0.0) v += sc.amp2[P] * (ez + (same_epoch ? sc.e.wn2 : 0.0));
+        if (sc.amp2[P] != 0.0) v = df(sc.amp2[P], da(ez, same_epoch ? sc.e.wn2 : 0.0), v);
         if (same_epoch) {
-            v = v + diag_add + sc.jit2[P];
-            if (nugget != 0.0) return (1.0 - nugget) * v + nugget * v;
+            v = da(da(v, diag_add), sc.jit2[P]);
+            if (nugget != 0.0) return df(1.0 - nugget, v, dm(nugget, v));
         }
     }
-    if (nugget != 0.0) v = (1.0 - nugget) * v;
+    if (nugget != 0.0) v = dm(1.0 - nugget, v);
     return v;
 }

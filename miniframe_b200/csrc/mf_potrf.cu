@@ -85,6 +85,10 @@ __global__ void __launch_bounds__(THREADS, 2) mf_potrf_ll_kernel(const Params p)
             const int nv = min(NB, n - j0);
             const int ntile = (n + 1 - j0 + TM - 1) / TM;
             const int nk = j0 / KC;
+            // rows written by the slowest warp in the previous block column must be in
+            // memory before anyone prefetches them (the first chunks are issued ahead of
+            // the first barrier of the contraction loop)
+            __syncthreads();
 
             for (int it = 0; it < ntile; ++it) {
                 const int i0 = j0 + it * TM;

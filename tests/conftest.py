@@ -48,9 +48,15 @@ def rel_err(a, b):
     return abs(a - b) / max(abs(b), 1e-300)
 
 
-def assert_matrix_parity(K, Kref, tri=None, rtol=1e-12, floor=1e-6):
-    """max|dK|/max|K| <= rtol and per entry
-    |dK_ij| <= rtol * max(|K_ij|, floor * max|K|)."""
+def assert_matrix_parity(K, Kref, tri=None, rtol=1e-12, floor=1e-4):
+    """max|dK|/max|K| <= rtol and per entry |dK_ij| <= rtol * max(|K_ij|, floor * max|K|).
+
+    Entries far below max|K| at lags where E is not small are differences of O(max|K|)
+    terms (zero crossings of Gdd, H, G4), so their absolute error is a few ulp of those
+    terms whatever the implementation; with floor = 1e-4 they are held to 1e-16 max|K|,
+    half an ulp of the largest entry (SURVEY.md section 8d proposed 1e-6, which two CPU
+    evaluations of the reference's own formulas already miss; measured on the B200:
+    N = 128, entry 1.2e-5 max|K|, |dK| = 2.4e-17 max|K|)."""
     K = np.asarray(K)
     Kref = np.asarray(Kref)
     assert K.shape == Kref.shape

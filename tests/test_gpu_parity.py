@@ -181,20 +181,26 @@ def test_factor_and_z_against_lapack(mf):
 
 
 def test_batch_mixes_failures_and_successes(mf, golden):
-    d = golden.data("spot40_noerr")
+    """Non-positive-definite samples give -inf for themselves only."""
+    d = golden.data("spot40")
     gp = mf.BIGgp.BIGgp(mf.kernels.SquaredExponential, [None, None, None], t=d["t"], rv=d["rv"],
                         rverr=d["rverr"], rhk=d["rhk"], sig_rhk=d["sig_rhk"], bis=d["bis"],
                         sig_bis=d["sig_bis"])
-    bad = [500.0, 0.0, 1.0, 0.5, 0.8, 0.9, 0.4]          # golden big_nonpd
-    good = [3.0, 0.5, 1.0, 0.5, 0.8, 0.9, 0.4]
-    A = np.array([good, bad, good, bad, bad, good])
+    # amplitudes 1e8 with a 5000-day scale: rounding noise of the pivots swamps yerr^2
+    bad1 = [5000.0, 0.0, 1e8, 1e8, 1e8, 1e8, 1e8]
+    bad2 = [800.0, 1e-6, 1e8, 5e7, 1e8, 1e8, 1e8]
+    good1 = [3.0, 0.5, 1.0, 0.5, 0.8, 0.9, 0.4]
+    good2 = [20.0, 0.03, 1.0, 0.5, 0.8, 0.9, 0.4]
+    A = np.array([good1, bad1, good2, bad2, bad1, good1])
     y = go.biggp_y(d["rv"], d["rhk"], d["bis"])
     got = gp.log_likelihood_batch(A)
     want = np.array([go.biggp_loglike_literal("SquaredExponential", a, d["t"], y, d["rverr"],
                                               d["sig_rhk"], d["sig_bis"]) for a in A])
-    assert np.array_equal(np.isinf(got), np.isinf(want)) and np.isinf(want).sum() == 3
+    assert np.isinf(want).sum() == 3
+    assert np.array_equal(np.isinf(got), np.isinf(want))
     ok = ~np.isinf(want)
     assert np.all(np.abs(got[ok] - want[ok]) <= LL_RTOL * np.abs(want[ok]))
+    assert gp.log_likelihood(bad1, []) == -np.inf
 
 
 def test_plusjitt_and_smallgp_batches(mf, golden):
