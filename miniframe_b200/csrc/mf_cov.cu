@@ -1,23 +1,34 @@
 // Fused covariance build (HBM-write bound): replaces compute_matrix() and the
 // 17 (BIGgp.py:172-278) / 9-per-block (SMALLgp.py:139-249) separate N x N
-// kernel-class evaluations of the reference with ONE sincos + ONE exp per
-// (i, j) lag, kept in registers and fanned out to every block (P, Q) that needs
-// it, written with coalesced 16-byte stores straight into the layout the
-// factorisation reads.  Times and the per-sample coefficient table are staged in
-// shared memory.
+// kernel-class evaluations of the reference.
+//
+//   * ONE sincos + ONE exp per UNORDERED pair of epochs {i, j}: the lag functions are
+//     even or odd (or, for the quirky third derivative, kept for both signs), so the
+//     value computed for (i, j) also gives (j, i).  A CTA owns 32 x 32 pair tiles with
+//     tile_i >= tile_j; the base functions stay in registers for the direct entries
+//     and cross one padded shared-memory tile for the transposed ones, so that every
+//     global store is a fully coalesced 256-byte row segment;
+//   * the base functions fan out to every block (P, Q) of the n x n matrix that needs
+//     them (6 blocks + 3 transposed blocks for BIGgp in lower mode = 9 outputs per
+//     transcendental evaluation; the reference does 17 evaluations for 9 blocks);
+//   * the per-sample coefficient table (kernel constants, block coefficients) is
+//     computed once per CTA and sample, in parallel over threads, and staged in shared
+//     memory together with the time arrays; a CTA walks many tiles of one sample.
 #include "mf_cov.cuh"
 
 namespace {
 
-constexpr int TI = 32;          // epoch rows per CTA tile
-constexpr int TJ = 64;          // epoch columns per CTA tile (2 per lane)
-constexpr int ROWS_PER_WARP = 4;
-constexpr int THREADS = 256;
+constexpr int TT = 32;           // pair-tile edge
+constexpr int THREADS = 256;     // 8 warps x 4 rows
+constexpr int RPW = 4;
+constexpr int TLD = 33;          // padded tile stride (doubles)
 
 struct CovParams {
     mf_problem_t prob;
     int batch;
     int full;
+    int tiles_per_dim;           // T = ceil(N / 32)
+    int n_tiles;                 // T (T + 1) / 2
     const double* t;
     const double* diag_add;
     const double* hyper;
@@ -30,69 +41,213 @@ struct CovParams {
 template <int KERNEL, bool HIGH>
 __global__ void __launch_bounds__(THREADS)
 mf_cov_build_kernel(const CovParams p) {
-    __shared__ SampleCoefs sc;
-    __shared__ double ti_s[TI];
-    __shared__ double tj_s[TJ];
+    extern __shared__ __align__(16) unsigned char cov_smem[];
+    SampleCoefs& sc = *reinterpret_cast<SampleCoefs*>(cov_smem);
+    constexpr int NBASE = HIGH ? 6 : 3;
+    double* const tiles = reinterpret_cast<double*>(cov_smem + ((sizeof(SampleCoefs) + 15) / 16) * 16);
+    double* const ti_s = tiles + NBASE * TT * TLD;
+    double* const tj_s = ti_s + TT;
 
     const int N = p.prob.n_epochs;
     const int M = p.prob.n_series;
-    const int tiles_j = (N + TJ - 1) / TJ;
-    const int tile_i = blockIdx.x / tiles_j;
-    const int tile_j = blockIdx.x % tiles_j;
-    const int i0 = tile_i * TI, j0 = tile_j * TJ;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double nugget = p.prob.nugget;
     const bool has_extra = p.prob.framework == MF_FRAMEWORK_SMALLGP &&
                            p.prob.extra_kernel != MF_KERNEL_NONE && M > 1;
-    const bool vec_base = ((N & 1) == 0) && ((p.ld & 1) == 0);
-
-    if (tid < TI) ti_s[tid] = (i0 + tid < N) ? p.t[i0 + tid] : 0.0;
-    if (tid >= 64 && tid < 64 + TJ) tj_s[tid - 64] = (j0 + tid - 64 < N) ? p.t[j0 + tid - 64] : 0.0;
+    const bool full = p.full != 0;
 
     for (int b = blockIdx.y; b < p.batch; b += gridDim.y) {
-        __syncthreads();   // previous sample's readers are done with sc
+        __syncthreads();                       // previous sample's readers are done with sc
+        if (tid == 0)
+            mf_make_coefs(p.prob, p.hyper + (size_t)b * p.prob.hyper_len,
+                          p.extra ? p.extra + (size_t)b * p.prob.extra_len : nullptr, sc);
+        double* const Kb = p.K + (size_t)b * p.stride;
+
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            // triangular index -> (tile_i >= tile_j)
+            int tile_i = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
+            while ((tile_i + 1) * (tile_i + 2) / 2 <= tile) ++tile_i;
+            while (tile_i * (tile_i + 1) / 2 > tile) --tile_i;
+            const int tile_j = tile - tile_i * (tile_i + 1) / 2;
+            const int i0 = tile_i * TT, j0 = tile_j * TT;
+            const bool diag_tile = tile_i == tile_j;
+
+            __syncthreads();                   // tiles / times of the previous tile are consumed
+            if (tid < TT) ti_s[tid] = (i0 + tid < N) ? p.t[i0 + tid] : 0.0;
+            if (tid >= 32 && tid < 32 + TT) tj_s[tid - 32] = (j0 + tid - 32 < N) ? p.t[j0 + tid - 32] : 0.0;
+            __syncthreads();
+
+            // ---- direct pass: lane <-> j, rows 4 warp + rr <-> i; entries (P N + i, Q N + j)
+            const int j = j0 + lane;
+            const double tj = tj_s[lane];
+#pragma unroll
+            for (int rr = 0; rr < RPW; ++rr) {
+                const int il = warp * RPW + rr;
+                const int i = i0 + il;
+                Bases bs;
+                const bool active = (i < N) && (j < N) && (!diag_tile || i >= j);
+                if (active) {
+                    const double r = ti_s[il] - tj;
+                    mf_bases<KERNEL, HIGH>(r, sc.k, bs);
+                    const double ez = has_extra ? mf_kernel_value(p.prob.extra_kernel, r, sc.e) : 0.0;
+                    const bool same = (i == j);
+                    for (int P = 0; P < M; ++P) {
+                        const double dadd = same ? p.diag_add[P * N + i] : 0.0;
+                        const int Qhi = full ? M : P + 1;
+                        for (int Q = 0; Q < Qhi; ++Q)
+                            Kb[(size_t)(P * N + i) * p.ld + (size_t)Q * N + j] =
+                                mf_entry(sc, bs, P, Q, same, ez, dadd, nugget);
+                    }
+                } else {
+                    bs.E = bs.AE = bs.Gdd = bs.Hf = bs.Hr = bs.G4 = 0.0;
+                }
+                double* tl = tiles + il * TLD + lane;
+                tl[0] = bs.E;
+                tl[TT * TLD] = bs.AE;
+                tl[2 * TT * TLD] = bs.Gdd;
+                if (HIGH) {
+                    tl[3 * TT * TLD] = bs.Hf;
+                    tl[4 * TT * TLD] = bs.Hr;
+                    tl[5 * TT * TLD] = bs.G4;
+                }
+            }
+            __syncthreads();
+
+            // ---- transposed pass: lane <-> i (now the column), rows 4 warp + rr <-> j (now the
+            // row); entries (P N + j, Q N + i) at lag t_j - t_i = -r: AE changes sign, H(r) and
+            // H(-r) swap.  Only pairs with i > j (the diagonal was written above).
+            const int ic = i0 + lane;
+#pragma unroll
+            for (int rr = 0; rr < RPW; ++rr) {
+                const int jl = warp * RPW + rr;
+                const int jr = j0 + jl;
+                if (ic < N && jr < N && ic > jr) {
+                    const double* tl = tiles + lane * TLD + jl;
+                    Bases bs;
+                    bs.E = tl[0];
+                    bs.AE = -tl[TT * TLD];
+                    bs.Gdd = tl[2 * TT * TLD];
+                    if (HIGH) {
+                        bs.Hf = tl[4 * TT * TLD];
+                        bs.Hr = tl[3 * TT * TLD];
+                        bs.G4 = tl[5 * TT * TLD];
+                    } else {
+                        bs.Hf = bs.Hr = bs.G4 = 0.0;
+                    }
+                    const double ez = has_extra ? mf_kernel_value(p.prob.extra_kernel, ti_s[lane] - tj_s[jl], sc.e) : 0.0;
+                    for (int P = 0; P < M; ++P) {
+                        // lower mode: the (j, i) entry lies above the diagonal of the n x n
+                        // matrix unless the row block is below the column block
+                        const int Qhi = full ? M : P;
+                        for (int Q = 0; Q < Qhi; ++Q)
+                            Kb[(size_t)(P * N + jr) * p.ld + (size_t)Q * N + ic] =
+                                mf_entry(sc, bs, P, Q, false, ez, 0.0, nugget);
+                    }
+                }
+            }
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------
+// Rajpaul (BIGgp / BIGgpPlusJitt) likelihood path: three series, lower triangle only,
+// no nugget (BIGgp.log_likelihood never applies one, BIGgp.py:300).  Same tiling and
+// the same operation order as the generic kernel (terms with a zero coefficient are
+// simply not issued, which leaves every bit unchanged), but the twelve non-zero block
+// coefficients live in registers, the nine outputs per pair are produced in one go and
+// only the three transposed VALUES cross shared memory.
+// ---------------------------------------------------------------------------------
+template <int KERNEL>
+__global__ void __launch_bounds__(THREADS)
+mf_cov_build_big_lower_kernel(const CovParams p) {
+    __shared__ SampleCoefs sc;
+    __shared__ double tiles[3 * TT * TLD];
+    __shared__ double ti_s[TT], tj_s[TT];
+
+    const int N = p.prob.n_epochs;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t ld = p.ld;
+    const int64_t o10 = (int64_t)N * ld, o20 = 2 * o10;          // row-block offsets
+    const int64_t o11 = o10 + N, o21 = o20 + N, o22 = o20 + 2 * N;
+
+    for (int b = blockIdx.y; b < p.batch; b += gridDim.y) {
+        __syncthreads();
         if (tid == 0)
             mf_make_coefs(p.prob, p.hyper + (size_t)b * p.prob.hyper_len,
                           p.extra ? p.extra + (size_t)b * p.prob.extra_len : nullptr, sc);
         __syncthreads();
-        double* Kb = p.K + (size_t)b * p.stride;
+        const double e00 = sc.c[0][0].cE, g00 = sc.c[0][0].cGdd;
+        const double e11 = sc.c[1][1].cE;
+        const double e22 = sc.c[2][2].cE, g22 = sc.c[2][2].cGdd;
+        const double e10 = sc.c[1][0].cE, a10 = sc.c[1][0].cAE;
+        const double e20 = sc.c[2][0].cE, g20 = sc.c[2][0].cGdd, a20 = sc.c[2][0].cAE;
+        const double e21 = sc.c[2][1].cE, a21 = sc.c[2][1].cAE;
+        double* const Kb = p.K + (size_t)b * p.stride;
 
-        const int jl = 2 * lane;
-        const int j = j0 + jl;
-        const bool j1ok = (j + 1 < N);
-        const double tj0 = tj_s[jl], tj1 = tj_s[jl + 1];
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            int tile_i = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
+            while ((tile_i + 1) * (tile_i + 2) / 2 <= tile) ++tile_i;
+            while (tile_i * (tile_i + 1) / 2 > tile) --tile_i;
+            const int tile_j = tile - tile_i * (tile_i + 1) / 2;
+            const int i0 = tile_i * TT, j0 = tile_j * TT;
+            const bool diag_tile = tile_i == tile_j;
 
+            __syncthreads();
+            if (tid < TT) ti_s[tid] = (i0 + tid < N) ? p.t[i0 + tid] : 0.0;
+            if (tid >= 32 && tid < 32 + TT) tj_s[tid - 32] = (j0 + tid - 32 < N) ? p.t[j0 + tid - 32] : 0.0;
+            __syncthreads();
+
+            const int j = j0 + lane;
+            const double tj = tj_s[lane];
 #pragma unroll
-        for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
-            const int il = warp * ROWS_PER_WARP + rr;
-            const int i = i0 + il;
-            if (i >= N || j >= N) break;
-            const double ti = ti_s[il];
-            Bases b0, b1;
-            mf_bases<KERNEL, HIGH>(ti - tj0, sc.k, b0);
-            mf_bases<KERNEL, HIGH>(ti - tj1, sc.k, b1);
-            double ez0 = 0.0, ez1 = 0.0;
-            if (has_extra) {
-                ez0 = mf_kernel_value(p.prob.extra_kernel, ti - tj0, sc.e);
-                ez1 = mf_kernel_value(p.prob.extra_kernel, ti - tj1, sc.e);
-            }
-            for (int P = 0; P < M; ++P) {
-                const int Qend = p.full ? M : P + 1;
-                const double dadd = p.diag_add[P * N + i];
-                for (int Q = 0; Q < Qend; ++Q) {
-                    // lower mode keeps (P > Q) blocks whole and the i >= j half of (P == P)
-                    const bool keep0 = p.full || P != Q || i >= j;
-                    const bool keep1 = j1ok && (p.full || P != Q || i >= j + 1);
-                    if (!keep0 && !keep1) continue;
-                    const double v0 = mf_entry(sc, b0, P, Q, i == j, ez0, dadd, nugget);
-                    const double v1 = mf_entry(sc, b1, P, Q, i == j + 1, ez1, dadd, nugget);
-                    double* dst = Kb + (size_t)(P * N + i) * p.ld + (size_t)Q * N + j;
-                    if (keep0 && keep1 && vec_base) {
-                        *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+            for (int rr = 0; rr < RPW; ++rr) {
+                const int il = warp * RPW + rr;
+                const int i = i0 + il;
+                double t10 = 0.0, t20 = 0.0, t21 = 0.0;
+                if ((i < N) && (j < N) && (!diag_tile || i >= j)) {
+                    Bases bs;
+                    mf_bases<KERNEL, false>(ti_s[il] - tj, sc.k, bs);
+                    double* dst = Kb + (size_t)i * ld + j;
+                    if (i != j) {
+                        dst[0] = df(g00, bs.Gdd, dm(e00, bs.E));
+                        dst[o11] = dm(e11, bs.E);
+                        dst[o22] = df(g22, bs.Gdd, dm(e22, bs.E));
+                        const double u10 = dm(e10, bs.E);
+                        const double u20 = df(g20, bs.Gdd, dm(e20, bs.E));
+                        const double u21 = dm(e21, bs.E);
+                        dst[o10] = df(a10, bs.AE, u10);
+                        dst[o20] = df(a20, bs.AE, u20);
+                        dst[o21] = df(a21, bs.AE, u21);
+                        t10 = df(a10, -bs.AE, u10);      // the same blocks at lag -r
+                        t20 = df(a20, -bs.AE, u20);
+                        t21 = df(a21, -bs.AE, u21);
                     } else {
-                        if (keep0) dst[0] = v0;
-                        if (keep1) dst[1] = v1;
+                        // same epoch: white noise on every block, errors and jitter on the diagonal
+                        for (int P = 0; P < 3; ++P)
+                            for (int Q = 0; Q <= P; ++Q)
+                                Kb[(size_t)(P * N + i) * ld + (size_t)Q * N + j] =
+                                    mf_entry(sc, bs, P, Q, true, 0.0, p.diag_add[P * N + i], 0.0);
                     }
+                }
+                double* tl = tiles + il * TLD + lane;
+                tl[0] = t10;
+                tl[TT * TLD] = t20;
+                tl[2 * TT * TLD] = t21;
+            }
+            __syncthreads();
+
+            const int ic = i0 + lane;
+#pragma unroll
+            for (int rr = 0; rr < RPW; ++rr) {
+                const int jl = warp * RPW + rr;
+                const int jr = j0 + jl;
+                if (ic < N && jr < N && ic > jr) {
+                    const double* tl = tiles + lane * TLD + jl;
+                    double* dst = Kb + (size_t)jr * ld + ic;
+                    dst[o10] = tl[0];
+                    dst[o20] = tl[TT * TLD];
+                    dst[o21] = tl[2 * TT * TLD];
                 }
             }
         }
@@ -103,10 +258,18 @@ mf_cov_build_kernel(const CovParams p) {
 
 template <int KERNEL, bool HIGH>
 static int launch_cov(mf_handle_t h, const CovParams& p, cudaStream_t st) {
-    const int N = p.prob.n_epochs;
-    const int tiles = ((N + TI - 1) / TI) * ((N + TJ - 1) / TJ);
-    dim3 grid(tiles, p.batch < 65535 ? p.batch : 65535);
-    mf_cov_build_kernel<KERNEL, HIGH><<<grid, THREADS, 0, st>>>(p);
+    const size_t smem = ((sizeof(SampleCoefs) + 15) / 16) * 16 +
+                        (size_t)((HIGH ? 6 : 3) * TT * TLD + 2 * TT) * sizeof(double);
+    MF_CUDA_CHECK(h, cudaFuncSetAttribute(mf_cov_build_kernel<KERNEL, HIGH>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // a CTA walks several tiles of one sample so the coefficient set-up is amortised; with
+    // few samples the tiles are spread over more CTAs to fill the 148 SMs
+    const int by = p.batch < 65535 ? p.batch : 65535;
+    int bx = (8 * h->sm_count + by - 1) / by;
+    if (bx < 1) bx = 1;
+    if (bx > p.n_tiles) bx = p.n_tiles;
+    dim3 grid(bx, by);
+    mf_cov_build_kernel<KERNEL, HIGH><<<grid, THREADS, smem, st>>>(p);
     MF_CUDA_CHECK(h, cudaGetLastError());
     return MF_OK;
 }
@@ -145,6 +308,8 @@ extern "C" int mf_build_cov(mf_handle_t h, const mf_problem_t* prob, int batch, 
     p.prob = *prob;
     p.batch = batch;
     p.full = full ? 1 : 0;
+    p.tiles_per_dim = (N + TT - 1) / TT;
+    p.n_tiles = p.tiles_per_dim * (p.tiles_per_dim + 1) / 2;
     p.t = t;
     p.diag_add = diag_add;
     p.hyper = hyper;
@@ -154,6 +319,19 @@ extern "C" int mf_build_cov(mf_handle_t h, const mf_problem_t* prob, int batch, 
     p.stride = stride;
     cudaStream_t st = (cudaStream_t)stream;
     const bool high = prob->framework == MF_FRAMEWORK_SMALLGP;
+    if (!high && !p.full && prob->nugget == 0.0) {
+        const int by = batch < 65535 ? batch : 65535;
+        int bx = (8 * h->sm_count + by - 1) / by;
+        if (bx < 1) bx = 1;
+        if (bx > p.n_tiles) bx = p.n_tiles;
+        dim3 grid(bx, by);
+        if (prob->kernel == MF_KERNEL_QP)
+            mf_cov_build_big_lower_kernel<MF_KERNEL_QP><<<grid, THREADS, 0, st>>>(p);
+        else
+            mf_cov_build_big_lower_kernel<MF_KERNEL_SE><<<grid, THREADS, 0, st>>>(p);
+        MF_CUDA_CHECK(h, cudaGetLastError());
+        return MF_OK;
+    }
     if (prob->kernel == MF_KERNEL_QP)
         return high ? launch_cov<MF_KERNEL_QP, true>(h, p, st) : launch_cov<MF_KERNEL_QP, false>(h, p, st);
     return high ? launch_cov<MF_KERNEL_SE, true>(h, p, st) : launch_cov<MF_KERNEL_SE, false>(h, p, st);

@@ -22,6 +22,7 @@
 //     z = L^-1 r, so the forward substitution costs one extra row in the last row
 //     tile, and -1/2 z.z - sum(log L_ii) - n/2 log(2 pi) falls out at the end.
 #include <math.h>
+#include <stdlib.h>
 
 #include "mf_common.cuh"
 
@@ -30,17 +31,19 @@ namespace pf {
 constexpr int TM = 128;       // rows per tile (8 warps x 16)
 constexpr int NB = 64;        // block-column width
 constexpr int KC = 16;        // contraction chunk per pipeline stage
-constexpr int NSTAGE = 2;
 constexpr int THREADS = 256;
 constexpr int STAGE_ROWS = TM + NB;
 constexpr int STAGE_BYTES = STAGE_ROWS * KC * 8;     // 24576
-constexpr int LD_LD = 72;     // doubles; 64 B mod 128 B -> conflict-free 16 B fragment loads
 constexpr int AW_LD = 65;
-constexpr int OFF_LD = NSTAGE * STAGE_BYTES;         // diagonal block L_jj
-constexpr int OFF_DINV = OFF_LD + NB * LD_LD * 8;    // inverses of its eight 8x8 diagonal blocks
-constexpr int OFF_RED = OFF_DINV + 8 * 64 * 8;
-constexpr int SMEM_BYTES = OFF_RED + 64 * 8;
-static_assert(NB * AW_LD * 8 <= NSTAGE * STAGE_BYTES, "potf2 work array must fit in the stage area");
+// L_jj is kept as its 36 lower 8x8 blocks, 512 B each (block (bi, bj) at bi(bi+1)/2 + bj):
+// a 16-byte fragment load of rows g, g+1 then covers one 128-byte line, conflict-free.
+constexpr int SZ_LD = 36 * 64 * 8;
+constexpr int SZ_DINV = 8 * 64 * 8;                  // minus-inverses of the 8 diagonal 8x8 blocks
+constexpr int SZ_COL = 2 * 72 * 8;                   // double-buffered scaled pivot column + status
+constexpr int SZ_RED = 64 * 8;
+constexpr int smem_bytes(int nstage) { return nstage * STAGE_BYTES + SZ_LD + SZ_DINV + SZ_COL + SZ_RED; }
+static_assert(NB * AW_LD * 8 <= 2 * STAGE_BYTES, "potf2 staging array must fit in the stage area");
+// 3 stages: 97,792 B, two CTAs per SM
 
 struct Params {
     int batch;
@@ -52,13 +55,28 @@ struct Params {
     int64_t resid_stride;
     double* ll;
     int32_t* info;
+    int sm_count;
+    long long* trace;     // DBG & 16: per-tile phase timestamps of the first matrix of each CTA
 };
 
-__global__ void __launch_bounds__(THREADS, 2) mf_potrf_ll_kernel(const Params p) {
+__device__ __forceinline__ double flip(double x) {      // -x on the integer pipe
+    return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x));
+}
+__device__ __forceinline__ int ldblk(int bi, int bj) { return (bi * (bi + 1) / 2 + bj) * 64; }
+
+// DBG (timing experiments only, results are garbage): 1 = no global->shared copies in the
+// contraction loop, 2 = no barriers there, 4 = no fragment loads there, 8 = no contraction at all
+template <int NSTAGE, int MINB, int DBG>
+__global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params p) {
+    constexpr int OFF_LD = NSTAGE * STAGE_BYTES;
+    constexpr int OFF_DINV = OFF_LD + SZ_LD;
+    constexpr int OFF_COL = OFF_DINV + SZ_DINV;
+    constexpr int OFF_RED = OFF_COL + SZ_COL;
     extern __shared__ __align__(128) unsigned char smem[];
     double* const Aw = reinterpret_cast<double*>(smem);                 // aliases the stages
     double* const Ld = reinterpret_cast<double*>(smem + OFF_LD);
     double* const Dinv = reinterpret_cast<double*>(smem + OFF_DINV);
+    double* const colbuf = reinterpret_cast<double*>(smem + OFF_COL);
     double* const red = reinterpret_cast<double*>(smem + OFF_RED);
     const uint32_t stage_u32 = smem_u32(smem);
 
@@ -72,11 +90,13 @@ __global__ void __launch_bounds__(THREADS, 2) mf_potrf_ll_kernel(const Params p)
     const uint32_t ldst = stage_u32 + lrow * 128 + ((lch ^ ((lrow & 1) << 2)) << 4);
     // fragment address inside a stage: 16-byte chunk (4h + t) of row r, swizzled by row parity
     const int fswz = (g & 1) << 2;
+    // potf2 ownership: rows tr + 16a, columns tc + 16b (a, b = 0..3) live in registers
+    const int tr = tid & 15, tc = tid >> 4;
 
     for (int mat = blockIdx.x; mat < p.batch; mat += gridDim.x) {
         double* const Kb = p.K + (size_t)mat * p.stride;
         const double* const rb = p.resid ? p.resid + (size_t)mat * p.resid_stride : nullptr;
-        double logdet = 0.0;
+        double logdet = 0.0;          // meaningful in warp 0 only
         int fail = 0;
         const int ncb = (n + NB - 1) / NB;
 
@@ -85,143 +105,229 @@ __global__ void __launch_bounds__(THREADS, 2) mf_potrf_ll_kernel(const Params p)
             const int nv = min(NB, n - j0);
             const int ntile = (n + 1 - j0 + TM - 1) / TM;
             const int nk = j0 / KC;
+            const int nicols = (nv + 7) >> 3;     // 8-column groups that hold real columns
             // rows written by the slowest warp in the previous block column must be in
             // memory before anyone prefetches them (the first chunks are issued ahead of
-            // the first barrier of the contraction loop)
+            // the first barrier of the contraction loop); also fences the stage area
             __syncthreads();
 
             for (int it = 0; it < ntile; ++it) {
                 const int i0 = j0 + it * TM;
+                const int wrow0 = i0 + 16 * warp;              // first row this warp owns
+                long long* tr_ = nullptr;
+                if ((DBG & 16) && mat == (int)blockIdx.x && tid == 0) {
+                    int tix = 0;
+                    for (int q = 0; q < jb; ++q) tix += (n + 1 - q * NB + TM - 1) / TM;
+                    tr_ = p.trace + ((size_t)blockIdx.x * 200 + tix + it) * 8;
+                    unsigned smid;
+                    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                    tr_[0] = smid; tr_[1] = jb * 1000 + it; tr_[2] = clock64();
+                }
+                // 8-column groups this warp has to produce: none if its rows lie beyond the
+                // residual row, only the lower triangle inside the diagonal block
+                int nilim = (wrow0 > n) ? 0 : nicols;
+                if (it == 0 && warp < 4) nilim = min(nilim, 2 * warp + 2);
 
-                auto load_stage = [&](int s, int kc) {
+                auto load_stage = [&](int s, int kc, int r0) {
                     const double* src_col = Kb + (size_t)kc * KC + lch * 2;
 #pragma unroll
                     for (int q = 0; q < 6; ++q) {
-                        const int grow = (q < 4) ? (i0 + lrow + 32 * q) : (j0 + lrow + 32 * (q - 4));
+                        const int grow = (q < 4) ? (r0 + lrow + 32 * q) : (j0 + lrow + 32 * (q - 4));
                         const bool ok = grow <= n;
                         const double* src = ok ? src_col + (size_t)grow * ld : Kb;
                         cp_async16(ldst + s * STAGE_BYTES + q * (32 * 128), src, ok ? 16 : 0);
                     }
                 };
 
-                if (nk > 0) {
-                    load_stage(0, 0);
-                    cp_async_commit();
+                // pipeline prologue: NSTAGE - 1 chunks in flight (groups may be empty); for
+                // every tile but the first of a block column it was issued before the
+                // previous tile's triangular solve
+                if (it == 0) {
+#pragma unroll
+                    for (int s0 = 0; s0 < NSTAGE - 1; ++s0) {
+                        if (s0 < nk) load_stage(s0, s0, i0);
+                        cp_async_commit();
+                    }
+                }
+                // pull the NEXT tile of K (same block column, else the head of the next one)
+                // into L2 while this tile is being contracted: one 512-byte row per thread
+                if (tid < TM) {
+                    const bool same = it + 1 < ntile;
+                    const int pj = same ? j0 : j0 + NB;
+                    const int prow = (same ? i0 + TM : j0 + NB) + tid;
+                    if (prow < n && pj < n) {
+                        const unsigned bytes = (unsigned)min(NB, (int)ld - pj) * 8u;
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Kb + (size_t)prow * ld + pj), "r"(bytes) : "memory");
+                    }
                 }
 
                 // accumulators start at -K(tile); the residual enters as row n
                 double acc[2][8][2];
+                const bool interior = (it > 0) && (i0 + TM <= n) && (j0 + NB <= n);
+                if (interior) {
 #pragma unroll
-                for (int mi = 0; mi < 2; ++mi) {
-                    const int row = i0 + 16 * warp + 8 * mi + g;
+                    for (int mi = 0; mi < 2; ++mi) {
+                        const double* src = Kb + (size_t)(wrow0 + 8 * mi + g) * ld + j0 + 2 * t;
 #pragma unroll
-                    for (int ni = 0; ni < 8; ++ni) {
-                        const int col = j0 + 8 * ni + 2 * t;
-                        double v0 = 0.0, v1 = 0.0;
-                        if (row < n) {
-                            if (col + 1 <= row && col + 1 < n) {
-                                const double2 v = *reinterpret_cast<const double2*>(Kb + (size_t)row * ld + col);
-                                v0 = v.x;
-                                v1 = v.y;
-                            } else if (col <= row && col < n) {
-                                v0 = Kb[(size_t)row * ld + col];
-                            }
-                        } else if (row == n && rb != nullptr) {
-                            if (col < n) v0 = rb[col];
-                            if (col + 1 < n) v1 = rb[col + 1];
+                        for (int ni = 0; ni < 8; ++ni) {
+                            const double2 v = *reinterpret_cast<const double2*>(src + 8 * ni);
+                            acc[mi][ni][0] = flip(v.x);
+                            acc[mi][ni][1] = flip(v.y);
                         }
-                        acc[mi][ni][0] = -v0;
-                        acc[mi][ni][1] = -v1;
+                    }
+                } else {
+#pragma unroll
+                    for (int mi = 0; mi < 2; ++mi) {
+                        const int row = wrow0 + 8 * mi + g;
+#pragma unroll
+                        for (int ni = 0; ni < 8; ++ni) {
+                            const int col = j0 + 8 * ni + 2 * t;
+                            double v0 = 0.0, v1 = 0.0;
+                            if (row < n) {
+                                if (col <= row && col < n) v0 = Kb[(size_t)row * ld + col];
+                                if (col + 1 <= row && col + 1 < n) v1 = Kb[(size_t)row * ld + col + 1];
+                            } else if (row == n && rb != nullptr) {
+                                if (col < n) v0 = rb[col];
+                                if (col + 1 < n) v1 = rb[col + 1];
+                            }
+                            acc[mi][ni][0] = flip(v0);
+                            acc[mi][ni][1] = flip(v1);
+                        }
                     }
                 }
 
+                if ((DBG & 16) && tr_) tr_[3] = clock64();
                 // ---- contraction over the finished columns k < j0 (tensor cores) ----
                 for (int kc = 0; kc < nk; ++kc) {
-                    if (kc + 1 < nk) {
-                        load_stage((kc + 1) & 1, kc + 1);
-                        cp_async_commit();
-                        cp_async_wait<1>();
-                    } else {
-                        cp_async_wait<0>();
-                    }
-                    __syncthreads();
-                    const unsigned char* sb = smem + (kc & 1) * STAGE_BYTES;
+                    if (DBG & 8) break;
+                    cp_async_wait<NSTAGE - 2>();  // chunk kc has landed
+                    if (!(DBG & 2)) __syncthreads();   // ... for everyone, and chunk kc-1 is consumed
+                    const unsigned char* sb = smem + (kc % NSTAGE) * STAGE_BYTES;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
+                        if (h == 1) {
+                            // refill the stage chunk kc-1 lived in; issued between the two halves
+                            // so the tensor pipe already has work queued while the copies go out
+                            if (!(DBG & 1) && kc + NSTAGE - 1 < nk) load_stage((kc + NSTAGE - 1) % NSTAGE, kc + NSTAGE - 1, i0);
+                            cp_async_commit();
+                        }
                         const int choff = ((4 * h + t) ^ fswz) << 4;
                         double2 a[2];
 #pragma unroll
                         for (int mi = 0; mi < 2; ++mi)
-                            a[mi] = *reinterpret_cast<const double2*>(sb + (16 * warp + 8 * mi + g) * 128 + choff);
+                            a[mi] = (DBG & 4) ? make_double2(1e-3 * kc, 1e-3)
+                                              : *reinterpret_cast<const double2*>(sb + (16 * warp + 8 * mi + g) * 128 + choff);
 #pragma unroll
-                        for (int ni = 0; ni < 8; ++ni) {
-                            const double2 b = *reinterpret_cast<const double2*>(sb + (TM + 8 * ni + g) * 128 + choff);
+                        for (int nq = 0; nq < 2; ++nq) {
+                            if (4 * nq < nilim) {
+                                double2 b[4];
 #pragma unroll
-                            for (int mi = 0; mi < 2; ++mi) {
-                                dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi].x, b.x);
-                                dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi].y, b.y);
+                                for (int u = 0; u < 4; ++u)
+                                    b[u] = (DBG & 4) ? make_double2(1e-3, 1e-3 * (kc + u))
+                                                     : *reinterpret_cast<const double2*>(sb + (TM + 8 * (4 * nq + u) + g) * 128 + choff);
+#pragma unroll
+                                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                                    for (int mi = 0; mi < 2; ++mi)
+                                        dmma884(acc[mi][4 * nq + u][0], acc[mi][4 * nq + u][1], a[mi].x, b[u].x);
+#pragma unroll
+                                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                                    for (int mi = 0; mi < 2; ++mi)
+                                        dmma884(acc[mi][4 * nq + u][0], acc[mi][4 * nq + u][1], a[mi].y, b[u].y);
                             }
                         }
                     }
-                    __syncthreads();
                 }
-
-                // acc = S - K  ->  C = K - S
-#pragma unroll
-                for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-                    for (int ni = 0; ni < 8; ++ni) {
-                        acc[mi][ni][0] = -acc[mi][ni][0];
-                        acc[mi][ni][1] = -acc[mi][ni][1];
-                    }
+                // acc now holds S - K = -C
+                __syncthreads();                  // the stage area is free again
+                if ((DBG & 16) && tr_) tr_[4] = clock64();
 
                 if (it == 0) {
-                    // ---- diagonal block: unblocked Cholesky of C[0:64, 0:64] in shared memory ----
-                    __syncthreads();
+                    // ---- diagonal block: Cholesky of C[0:64, 0:64], one barrier per column ----
                     if (warp < 4) {
 #pragma unroll
                         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
                             for (int ni = 0; ni < 8; ++ni) {
                                 double* d = Aw + (16 * warp + 8 * mi + g) * AW_LD + 8 * ni + 2 * t;
-                                d[0] = acc[mi][ni][0];
-                                d[1] = acc[mi][ni][1];
+                                d[0] = flip(acc[mi][ni][0]);
+                                d[1] = flip(acc[mi][ni][1]);
                             }
                     }
-                    const int r = tid & 63, kg = tid >> 6;
-                    for (int c = 0; c < nv; ++c) {
-                        __syncthreads();
-                        const double d = Aw[c * AW_LD + c];
-                        if (!(d > 0.0)) {       // LAPACK dpotrf: info = index of the failing pivot
-                            fail = j0 + c + 1;
-                            break;
+                    __syncthreads();
+                    double e[4][4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) e[a][b] = Aw[(tr + 16 * a) * AW_LD + tc + 16 * b];
+#pragma unroll
+                    for (int cb = 0; cb < 4; ++cb) {
+                        for (int cl = 0; cl < 16; ++cl) {
+                            const int c = 16 * cb + cl;
+                            if (c >= nv) break;
+                            double* col = colbuf + (c & 1) * 72;
+                            if (tc == cl) {
+                                // the 16 threads that own column c sit in one half-warp; lane cl of
+                                // it owns the pivot
+                                const double d = __shfl_sync(0xffffu << (16 * (lane >> 4)), e[cb][cb], (lane & 16) + cl);
+                                const bool bad = !DBG && !(d > 0.0);   // LAPACK dpotrf pivot test
+                                const double rs = bad ? 0.0 : rsqrt(d);
+                                if (tr == cl) col[64] = bad ? -1.0 : 1.0;
+#pragma unroll
+                                for (int a = 0; a < 4; ++a) {
+                                    const int r = tr + 16 * a;
+                                    const double v = (r > c) ? e[a][cb] * rs : (r == c ? d * rs : 0.0);
+                                    col[r] = v;
+                                    if ((r >> 3) >= (c >> 3)) Ld[ldblk(r >> 3, c >> 3) + (r & 7) * 8 + (c & 7)] = v;
+                                }
+                            }
+                            __syncthreads();
+                            if (col[64] < 0.0) {
+                                fail = j0 + c + 1;
+                                break;
+                            }
+                            double lr[4], lk[4];
+#pragma unroll
+                            for (int a = 0; a < 4; ++a) lr[a] = col[tr + 16 * a];
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) lk[b] = col[tc + 16 * b];
+#pragma unroll
+                            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                                for (int b = 0; b < 4; ++b)
+                                    if (b >= cb && tc + 16 * b > c && tr + 16 * a >= tc + 16 * b)
+                                        e[a][b] = fma(-lr[a], lk[b], e[a][b]);
                         }
-                        const double s = sqrt(d);
-                        const double inv = 1.0 / s;
-                        logdet += log(s);
-                        const double lr = Aw[r * AW_LD + c] * inv;
-                        if (kg == 0) Ld[r * LD_LD + c] = (r > c) ? lr : (r == c ? s : 0.0);
-                        if (r > c)
-                            for (int k = c + 1 + kg; k <= r; k += 4)
-                                Aw[r * AW_LD + k] -= lr * (Aw[k * AW_LD + c] * inv);
+                        if (fail) break;
                     }
                     if (fail) break;
-                    for (int c = nv + kg; c < NB; c += 4) Ld[r * LD_LD + c] = (r == c) ? 1.0 : 0.0;
+                    // columns beyond the matrix order: identity, keeps the 8x8 inverses finite
+                    if (tid < 64)
+                        for (int c = nv; c < NB; ++c)
+                            if ((tid >> 3) >= (c >> 3))
+                                Ld[ldblk(tid >> 3, c >> 3) + (tid & 7) * 8 + (c & 7)] = (tid == c) ? 1.0 : 0.0;
                     __syncthreads();
                     if (tid < 64) {
-                        // column cc of the inverse of the 8x8 diagonal block bb of L_jj
+                        // column cc of MINUS the inverse of the 8x8 diagonal block bb of L_jj
                         const int bb = tid >> 3, cc = tid & 7;
-                        const double* Lb = Ld + (8 * bb) * LD_LD + 8 * bb;
+                        const double* Lb = Ld + ldblk(bb, bb);
                         double x[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            double sum = (i == cc) ? 1.0 : 0.0;
+                            double sum = (i == cc) ? -1.0 : 0.0;
 #pragma unroll
-                            for (int k = 0; k < i; ++k) sum -= Lb[i * LD_LD + k] * x[k];
-                            x[i] = sum / Lb[i * LD_LD + i];
+                            for (int k = 0; k < i; ++k) sum -= Lb[i * 8 + k] * x[k];
+                            x[i] = sum / Lb[i * 8 + i];
                         }
 #pragma unroll
                         for (int i = 0; i < 8; ++i) Dinv[bb * 64 + i * 8 + cc] = x[i];
+                    }
+                    if (warp == 0) {              // sum of log L_ii of this block
+                        double lg = 0.0;
+                        if (lane < nv) lg += log(Ld[ldblk(lane >> 3, lane >> 3) + (lane & 7) * 9]);
+                        if (lane + 32 < nv) lg += log(Ld[ldblk((lane + 32) >> 3, (lane + 32) >> 3) + (lane & 7) * 9]);
+                        logdet += warp_sum(lg);
                     }
                     // L_jj (and, when the block column is the last one, the z entries that
                     // live inside it) go back to global memory, one 512-byte row per warp pass
@@ -231,18 +337,34 @@ __global__ void __launch_bounds__(THREADS, 2) mf_potrf_ll_kernel(const Params p)
                         const int rr = idx >> 5, cp = (idx & 31) * 2;
                         const int row = j0 + rr, col = j0 + cp;
                         if (row <= n && col < n) {
+                            double2 v = make_double2(0.0, 0.0);
+                            if ((cp >> 3) <= (rr >> 3))
+                                v = *reinterpret_cast<const double2*>(Ld + ldblk(rr >> 3, cp >> 3) + (rr & 7) * 8 + (cp & 7));
                             double* dst = Kb + (size_t)row * ld + col;
                             if (col + 1 < n)
-                                *reinterpret_cast<double2*>(dst) = make_double2(Ld[rr * LD_LD + cp], Ld[rr * LD_LD + cp + 1]);
+                                *reinterpret_cast<double2*>(dst) = v;
                             else
-                                dst[0] = Ld[rr * LD_LD + cp];
+                                dst[0] = v.x;
                         }
                     }
                     __syncthreads();
-                    if (warp < 4) continue;     // rows of the diagonal block are done
                 }
+                // the stage area is idle from here to the next contraction loop: start the next
+                // tile's first chunks now so they land while the triangular solve runs
+                if (it + 1 < ntile) {
+#pragma unroll
+                    for (int s0 = 0; s0 < NSTAGE - 1; ++s0) {
+                        if (s0 < nk) load_stage(s0, s0, i0 + TM);
+                        cp_async_commit();
+                    }
+                }
+                if ((DBG & 16) && tr_) tr_[5] = clock64();
+                if (it == 0 && warp < 4) continue;   // rows of the diagonal block are done
+                if (wrow0 > n) continue;             // nothing real in this warp's rows
 
-                // ---- X = C L_jj^-T on the tensor cores, 8-column blocks, in registers ----
+                // ---- X = C L_jj^-T on the tensor cores, 8-column blocks, in registers.
+                // acc holds -C; Dinv holds -inv(L_bb), so x = acc Dinv^T = +X, and the later
+                // column groups (still negated) absorb +X L^T ----
 #pragma unroll
                 for (int nb = 0; nb < 8; ++nb) {
                     const double2 dv = *reinterpret_cast<const double2*>(Dinv + nb * 64 + g * 8 + 2 * t);
@@ -256,11 +378,11 @@ __global__ void __launch_bounds__(THREADS, 2) mf_potrf_ll_kernel(const Params p)
                     }
 #pragma unroll
                     for (int nb2 = nb + 1; nb2 < 8; ++nb2) {
-                        const double2 lv = *reinterpret_cast<const double2*>(Ld + (8 * nb2 + g) * LD_LD + 8 * nb + 2 * t);
+                        const double2 lv = *reinterpret_cast<const double2*>(Ld + ldblk(nb2, nb) + g * 8 + 2 * t);
 #pragma unroll
                         for (int mi = 0; mi < 2; ++mi) {
-                            dmma884(acc[mi][nb2][0], acc[mi][nb2][1], -acc[mi][nb][0], lv.x);
-                            dmma884(acc[mi][nb2][0], acc[mi][nb2][1], -acc[mi][nb][1], lv.y);
+                            dmma884(acc[mi][nb2][0], acc[mi][nb2][1], acc[mi][nb][0], lv.x);
+                            dmma884(acc[mi][nb2][0], acc[mi][nb2][1], acc[mi][nb][1], lv.y);
                         }
                     }
                 }
@@ -268,7 +390,7 @@ __global__ void __launch_bounds__(THREADS, 2) mf_potrf_ll_kernel(const Params p)
                 // ---- rows of L (and z) are final: write them once ----
 #pragma unroll
                 for (int mi = 0; mi < 2; ++mi) {
-                    const int row = i0 + 16 * warp + 8 * mi + g;
+                    const int row = wrow0 + 8 * mi + g;
                     if (row <= n) {
 #pragma unroll
                         for (int ni = 0; ni < 8; ++ni) {
@@ -315,9 +437,6 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
     if (ld < n || (ld % 16) != 0) MF_FAIL(h, MF_ERR_INVALID, "ld must be a multiple of 16 and >= n");
     if (stride < (int64_t)(n + 1) * ld) MF_FAIL(h, MF_ERR_INVALID, "stride must cover n + 1 rows");
     if (((uintptr_t)K & 15) != 0) MF_FAIL(h, MF_ERR_INVALID, "K must be 16-byte aligned");
-    MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          pf::SMEM_BYTES));
     pf::Params p;
     p.batch = batch;
     p.n = n;
@@ -328,9 +447,76 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
     p.resid_stride = resid_stride;
     p.ll = ll;
     p.info = info;
-    const int slots = 2 * h->sm_count;
+    p.sm_count = h->sm_count;
+    const char* es = getenv("MF_SLOTS_PER_SM");
+    const char* en = getenv("MF_NSTAGE");
+    const int per_sm = es ? atoi(es) : 2;
+    const int nstage = en ? atoi(en) : 3;
+    const int slots = per_sm * h->sm_count;
     const int grid = batch < slots ? batch : slots;
-    pf::mf_potrf_ll_kernel<<<grid, pf::THREADS, pf::SMEM_BYTES, (cudaStream_t)stream>>>(p);
+    cudaStream_t st = (cudaStream_t)stream;
+#define MF_LAUNCH(NS, MB)                                                                          \
+    do {                                                                                           \
+        MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<NS, MB, DBG_>,                \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                              pf::smem_bytes(NS)));                                \
+        pf::mf_potrf_ll_kernel<NS, MB, DBG_><<<grid, pf::THREADS, pf::smem_bytes(NS), st>>>(p);    \
+    } while (0)
+    const char* ed = getenv("MF_DBG");
+    const int dbg = ed ? atoi(ed) : 0;
+    p.trace = nullptr;
+    if (dbg == 16) {
+        const size_t words = (size_t)grid * 200 * 8;
+        MF_CUDA_CHECK(h, cudaMalloc(&p.trace, words * 8));
+        MF_CUDA_CHECK(h, cudaMemsetAsync(p.trace, 0, words * 8, st));
+#define DBG_ 16
+        MF_LAUNCH(3, 2);
+#undef DBG_
+        MF_CUDA_CHECK(h, cudaStreamSynchronize(st));
+        long long* host = (long long*)malloc(words * 8);
+        MF_CUDA_CHECK(h, cudaMemcpy(host, p.trace, words * 8, cudaMemcpyDeviceToHost));
+        const char* path = getenv("MF_TRACE");
+        FILE* f = fopen(path ? path : "gpurun_out/potrf_trace.bin", "wb");
+        if (f) { fwrite(host, 8, words, f); fclose(f); }
+        free(host);
+        cudaFree(p.trace);
+        return MF_OK;
+    }
+    if (dbg) {
+#define DBG_ 1
+        if (dbg == 1) MF_LAUNCH(3, 2);
+#undef DBG_
+#define DBG_ 2
+        if (dbg == 2) MF_LAUNCH(3, 2);
+#undef DBG_
+#define DBG_ 3
+        if (dbg == 3) MF_LAUNCH(3, 2);
+#undef DBG_
+#define DBG_ 7
+        if (dbg == 7) MF_LAUNCH(3, 2);
+#undef DBG_
+#define DBG_ 8
+        if (dbg == 8) MF_LAUNCH(3, 2);
+#undef DBG_
+#define DBG_ 4
+        if (dbg == 4) MF_LAUNCH(3, 2);
+#undef DBG_
+        MF_CUDA_CHECK(h, cudaGetLastError());
+        return MF_OK;
+    }
+#define DBG_ 0
+    if (per_sm >= 2) {
+        MF_LAUNCH(3, 2);
+    } else {
+        switch (nstage) {
+            case 4: MF_LAUNCH(4, 1); break;
+            case 6: MF_LAUNCH(6, 1); break;
+            case 8: MF_LAUNCH(8, 1); break;
+            default: MF_LAUNCH(3, 1); break;
+        }
+    }
+#undef MF_LAUNCH
+#undef DBG_
     MF_CUDA_CHECK(h, cudaGetLastError());
     return MF_OK;
 }
