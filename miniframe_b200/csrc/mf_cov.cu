@@ -159,17 +159,21 @@ mf_cov_build_kernel(const CovParams p) {
 // only the three transposed VALUES cross shared memory.
 // ---------------------------------------------------------------------------------
 template <int KERNEL>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 3)
 mf_cov_build_big_lower_kernel(const CovParams p) {
-    __shared__ SampleCoefs sc;
-    __shared__ double tiles[3 * TT * TLD];
-    __shared__ double ti_s[TT], tj_s[TT];
+    extern __shared__ __align__(16) unsigned char big_smem[];
+    SampleCoefs& sc = *reinterpret_cast<SampleCoefs*>(big_smem);
+    // two sets of three transposition tiles: one barrier per pair tile
+    double* const tiles = reinterpret_cast<double*>(big_smem + ((sizeof(SampleCoefs) + 15) / 16) * 16);
+    double* const t_s = tiles + 2 * 3 * TT * TLD;        // the whole time array, staged once
 
     const int N = p.prob.n_epochs;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t ld = p.ld;
     const int64_t o10 = (int64_t)N * ld, o20 = 2 * o10;          // row-block offsets
     const int64_t o11 = o10 + N, o21 = o20 + N, o22 = o20 + 2 * N;
+
+    for (int k = tid; k < N; k += THREADS) t_s[k] = p.t[k];
 
     for (int b = blockIdx.y; b < p.batch; b += gridDim.y) {
         __syncthreads();
@@ -185,21 +189,42 @@ mf_cov_build_big_lower_kernel(const CovParams p) {
         const double e21 = sc.c[2][1].cE, a21 = sc.c[2][1].cAE;
         double* const Kb = p.K + (size_t)b * p.stride;
 
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            int tile_i = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
-            while ((tile_i + 1) * (tile_i + 2) / 2 <= tile) ++tile_i;
-            while (tile_i * (tile_i + 1) / 2 > tile) --tile_i;
-            const int tile_j = tile - tile_i * (tile_i + 1) / 2;
-            const int i0 = tile_i * TT, j0 = tile_j * TT;
-            const bool diag_tile = tile_i == tile_j;
-
-            __syncthreads();
-            if (tid < TT) ti_s[tid] = (i0 + tid < N) ? p.t[i0 + tid] : 0.0;
-            if (tid >= 32 && tid < 32 + TT) tj_s[tid - 32] = (j0 + tid - 32 < N) ? p.t[j0 + tid - 32] : 0.0;
-            __syncthreads();
-
+        int prev_i0 = -1, prev_j0 = 0, par = 0;
+        for (int tile = blockIdx.x;; tile += gridDim.x) {
+            const bool have = tile < p.n_tiles;
+            int i0 = 0, j0 = 0;
+            bool diag_tile = false;
+            if (have) {
+                int tile_i = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
+                while ((tile_i + 1) * (tile_i + 2) / 2 <= tile) ++tile_i;
+                while (tile_i * (tile_i + 1) / 2 > tile) --tile_i;
+                const int tile_j = tile - tile_i * (tile_i + 1) / 2;
+                i0 = tile_i * TT;
+                j0 = tile_j * TT;
+                diag_tile = tile_i == tile_j;
+            }
+            // ---- transposed stores of the PREVIOUS tile: lane <-> i (column), row <-> j
+            if (prev_i0 >= 0) {
+                const double* tb = tiles + (par ^ 1) * 3 * TT * TLD;
+                const int ic = prev_i0 + lane;
+#pragma unroll
+                for (int rr = 0; rr < RPW; ++rr) {
+                    const int jl = warp * RPW + rr;
+                    const int jr = prev_j0 + jl;
+                    if (ic < N && jr < N && ic > jr) {
+                        const double* tl = tb + lane * TLD + jl;
+                        double* dst = Kb + (size_t)jr * ld + ic;
+                        dst[o10] = tl[0];
+                        dst[o20] = tl[TT * TLD];
+                        dst[o21] = tl[2 * TT * TLD];
+                    }
+                }
+            }
+            if (!have) break;
+            // ---- direct pass of this tile: lane <-> j, rows 4 warp + rr <-> i
+            double* const tw = tiles + par * 3 * TT * TLD;
             const int j = j0 + lane;
-            const double tj = tj_s[lane];
+            const double tj = (j < N) ? t_s[j] : 0.0;
 #pragma unroll
             for (int rr = 0; rr < RPW; ++rr) {
                 const int il = warp * RPW + rr;
@@ -207,7 +232,7 @@ mf_cov_build_big_lower_kernel(const CovParams p) {
                 double t10 = 0.0, t20 = 0.0, t21 = 0.0;
                 if ((i < N) && (j < N) && (!diag_tile || i >= j)) {
                     Bases bs;
-                    mf_bases<KERNEL, false>(ti_s[il] - tj, sc.k, bs);
+                    mf_bases<KERNEL, false>(t_s[i] - tj, sc.k, bs);
                     double* dst = Kb + (size_t)i * ld + j;
                     if (i != j) {
                         dst[0] = df(g00, bs.Gdd, dm(e00, bs.E));
@@ -230,26 +255,15 @@ mf_cov_build_big_lower_kernel(const CovParams p) {
                                     mf_entry(sc, bs, P, Q, true, 0.0, p.diag_add[P * N + i], 0.0);
                     }
                 }
-                double* tl = tiles + il * TLD + lane;
+                double* tl = tw + il * TLD + lane;
                 tl[0] = t10;
                 tl[TT * TLD] = t20;
                 tl[2 * TT * TLD] = t21;
             }
-            __syncthreads();
-
-            const int ic = i0 + lane;
-#pragma unroll
-            for (int rr = 0; rr < RPW; ++rr) {
-                const int jl = warp * RPW + rr;
-                const int jr = j0 + jl;
-                if (ic < N && jr < N && ic > jr) {
-                    const double* tl = tiles + lane * TLD + jl;
-                    double* dst = Kb + (size_t)jr * ld + ic;
-                    dst[o10] = tl[0];
-                    dst[o20] = tl[TT * TLD];
-                    dst[o21] = tl[2 * TT * TLD];
-                }
-            }
+            __syncthreads();          // tile buffer `par` complete; buffer `par ^ 1` fully read
+            prev_i0 = i0;
+            prev_j0 = j0;
+            par ^= 1;
         }
     }
 }
@@ -325,10 +339,18 @@ extern "C" int mf_build_cov(mf_handle_t h, const mf_problem_t* prob, int batch, 
         if (bx < 1) bx = 1;
         if (bx > p.n_tiles) bx = p.n_tiles;
         dim3 grid(bx, by);
-        if (prob->kernel == MF_KERNEL_QP)
-            mf_cov_build_big_lower_kernel<MF_KERNEL_QP><<<grid, THREADS, 0, st>>>(p);
-        else
-            mf_cov_build_big_lower_kernel<MF_KERNEL_SE><<<grid, THREADS, 0, st>>>(p);
+        const size_t smem = ((sizeof(SampleCoefs) + 15) / 16) * 16 +
+                            (size_t)(2 * 3 * TT * TLD + N) * sizeof(double);
+        if (smem > h->smem_optin) MF_FAIL(h, MF_ERR_UNSUPPORTED, "n_epochs %d too large for the staged time array", N);
+        if (prob->kernel == MF_KERNEL_QP) {
+            MF_CUDA_CHECK(h, cudaFuncSetAttribute(mf_cov_build_big_lower_kernel<MF_KERNEL_QP>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            mf_cov_build_big_lower_kernel<MF_KERNEL_QP><<<grid, THREADS, smem, st>>>(p);
+        } else {
+            MF_CUDA_CHECK(h, cudaFuncSetAttribute(mf_cov_build_big_lower_kernel<MF_KERNEL_SE>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            mf_cov_build_big_lower_kernel<MF_KERNEL_SE><<<grid, THREADS, smem, st>>>(p);
+        }
         MF_CUDA_CHECK(h, cudaGetLastError());
         return MF_OK;
     }

@@ -40,7 +40,7 @@ constexpr int AW_LD = 65;
 constexpr int SZ_LD = 36 * 64 * 8;
 constexpr int SZ_DINV = 8 * 64 * 8;                  // minus-inverses of the 8 diagonal 8x8 blocks
 constexpr int SZ_COL = 2 * 72 * 8;                   // double-buffered scaled pivot column + status
-constexpr int SZ_RED = 64 * 8;
+constexpr int SZ_RED = 64 * 8;                       // reduction scratch + 2 x NSTAGE mbarriers
 constexpr int smem_bytes(int nstage) { return nstage * STAGE_BYTES + SZ_LD + SZ_DINV + SZ_COL + SZ_RED; }
 static_assert(NB * AW_LD * 8 <= 2 * STAGE_BYTES, "potf2 staging array must fit in the stage area");
 // 3 stages: 97,792 B, two CTAs per SM
@@ -64,8 +64,29 @@ __device__ __forceinline__ double flip(double x) {      // -x on the integer pip
 }
 __device__ __forceinline__ int ldblk(int bi, int bj) { return (bi * (bi + 1) / 2 + bj) * 64; }
 
-// DBG (timing experiments only, results are garbage): 1 = no global->shared copies in the
-// contraction loop, 2 = no barriers there, 4 = no fragment loads there, 8 = no contraction at all
+// ---- mbarrier primitives (shared::cta) ---------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "MF_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra MF_WAIT_%=;\n\t}"
+        ::"r"(bar), "r"(parity)
+        : "memory");
+}
+// arrive on `bar` once all cp.async copies this thread has issued so far have landed
+__device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// DBG (timing experiments only): 8 = skip the contraction loop (results are garbage),
+// 16 = record per-tile phase timestamps of the first matrix of every CTA
 template <int NSTAGE, int MINB, int DBG>
 __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params p) {
     constexpr int OFF_LD = NSTAGE * STAGE_BYTES;
@@ -92,6 +113,24 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params
     const int fswz = (g & 1) << 2;
     // potf2 ownership: rows tr + 16a, columns tc + 16b (a, b = 0..3) live in registers
     const int tr = tid & 15, tc = tid >> 4;
+
+    // producer/consumer ring over the stages, no CTA-wide barrier in the contraction loop:
+    //   full[s]  - 256 arrivals, one per thread, raised by the copy engine when that thread's
+    //              cp.async copies into stage s have landed;
+    //   empty[s] - 8 arrivals, one per warp, after the warp's last fragment load from stage s.
+    // Chunks are numbered over the whole kernel lifetime (gfill issued, guse consumed):
+    // chunk c lives in stage c % NSTAGE and is that stage's (c / NSTAGE)-th use.
+    const uint32_t bar_full = smem_u32(smem + OFF_RED + 256);
+    const uint32_t bar_empty = bar_full + 8 * NSTAGE;
+    if (tid == 0) {
+        for (int s0 = 0; s0 < NSTAGE; ++s0) {
+            mbar_init(bar_full + 8 * s0, THREADS);
+            mbar_init(bar_empty + 8 * s0, THREADS / 32);
+        }
+    }
+    __syncthreads();
+    uint32_t fill_s = 0, fill_k = 0;      // stage / use count of the next chunk to issue
+    uint32_t use_s = 0, use_k = 0;        // ... of the next chunk to consume
 
     for (int mat = blockIdx.x; mat < p.batch; mat += gridDim.x) {
         double* const Kb = p.K + (size_t)mat * p.stride;
@@ -128,26 +167,30 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params
                 int nilim = (wrow0 > n) ? 0 : nicols;
                 if (it == 0 && warp < 4) nilim = min(nilim, 2 * warp + 2);
 
-                auto load_stage = [&](int s, int kc, int r0) {
+                auto issue_chunk = [&](int kc, int r0) {
+                    // wait until every warp has released the previous use of this stage
+                    if (fill_k > 0) mbar_wait(bar_empty + 8 * fill_s, (fill_k - 1) & 1);
                     const double* src_col = Kb + (size_t)kc * KC + lch * 2;
 #pragma unroll
                     for (int q = 0; q < 6; ++q) {
                         const int grow = (q < 4) ? (r0 + lrow + 32 * q) : (j0 + lrow + 32 * (q - 4));
                         const bool ok = grow <= n;
                         const double* src = ok ? src_col + (size_t)grow * ld : Kb;
-                        cp_async16(ldst + s * STAGE_BYTES + q * (32 * 128), src, ok ? 16 : 0);
+                        cp_async16(ldst + fill_s * STAGE_BYTES + q * (32 * 128), src, ok ? 16 : 0);
+                    }
+                    cp_async_mbar_arrive(bar_full + 8 * fill_s);
+                    if (++fill_s == NSTAGE) {
+                        fill_s = 0;
+                        ++fill_k;
                     }
                 };
 
-                // pipeline prologue: NSTAGE - 1 chunks in flight (groups may be empty); for
-                // every tile but the first of a block column it was issued before the
-                // previous tile's triangular solve
+                // pipeline prologue: up to NSTAGE - 1 chunks in flight; for every tile but the
+                // first of a block column it was issued before the previous tile's triangular solve
                 if (it == 0) {
 #pragma unroll
-                    for (int s0 = 0; s0 < NSTAGE - 1; ++s0) {
-                        if (s0 < nk) load_stage(s0, s0, i0);
-                        cp_async_commit();
-                    }
+                    for (int s0 = 0; s0 < NSTAGE - 1; ++s0)
+                        if (s0 < nk) issue_chunk(s0, i0);
                 }
                 // pull the NEXT tile of K (same block column, else the head of the next one)
                 // into L2 while this tile is being contracted: one 512-byte row per thread
@@ -199,32 +242,42 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params
                 if ((DBG & 16) && tr_) tr_[3] = clock64();
                 // ---- contraction over the finished columns k < j0 (tensor cores) ----
                 for (int kc = 0; kc < nk; ++kc) {
-                    if (DBG & 8) break;
-                    cp_async_wait<NSTAGE - 2>();  // chunk kc has landed
-                    if (!(DBG & 2)) __syncthreads();   // ... for everyone, and chunk kc-1 is consumed
-                    const unsigned char* sb = smem + (kc % NSTAGE) * STAGE_BYTES;
+                    if (DBG & 8) {          // timing experiment: consume the ring without computing
+                        mbar_wait(bar_full + 8 * use_s, use_k & 1);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_empty + 8 * use_s);
+                        if (kc + NSTAGE - 1 < nk) issue_chunk(kc + NSTAGE - 1, i0);
+                        if (++use_s == NSTAGE) { use_s = 0; ++use_k; }
+                        continue;
+                    }
+                    mbar_wait(bar_full + 8 * use_s, use_k & 1);      // chunk kc has landed
+                    const unsigned char* sb = smem + use_s * STAGE_BYTES;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         if (h == 1) {
-                            // refill the stage chunk kc-1 lived in; issued between the two halves
-                            // so the tensor pipe already has work queued while the copies go out
-                            if (!(DBG & 1) && kc + NSTAGE - 1 < nk) load_stage((kc + NSTAGE - 1) % NSTAGE, kc + NSTAGE - 1, i0);
-                            cp_async_commit();
+                            // refill the ring two chunks ahead; issued between the two halves so
+                            // the tensor pipe already has work queued while the copies go out
+                            if (kc + NSTAGE - 1 < nk) issue_chunk(kc + NSTAGE - 1, i0);
                         }
                         const int choff = ((4 * h + t) ^ fswz) << 4;
                         double2 a[2];
 #pragma unroll
                         for (int mi = 0; mi < 2; ++mi)
-                            a[mi] = (DBG & 4) ? make_double2(1e-3 * kc, 1e-3)
-                                              : *reinterpret_cast<const double2*>(sb + (16 * warp + 8 * mi + g) * 128 + choff);
+                            a[mi] = *reinterpret_cast<const double2*>(sb + (16 * warp + 8 * mi + g) * 128 + choff);
 #pragma unroll
                         for (int nq = 0; nq < 2; ++nq) {
+                            double2 b[4];
                             if (4 * nq < nilim) {
-                                double2 b[4];
 #pragma unroll
                                 for (int u = 0; u < 4; ++u)
-                                    b[u] = (DBG & 4) ? make_double2(1e-3, 1e-3 * (kc + u))
-                                                     : *reinterpret_cast<const double2*>(sb + (TM + 8 * (4 * nq + u) + g) * 128 + choff);
+                                    b[u] = *reinterpret_cast<const double2*>(sb + (TM + 8 * (4 * nq + u) + g) * 128 + choff);
+                            }
+                            if (h == 1 && nq == 1) {
+                                // last fragment load of this chunk: hand the stage back
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(bar_empty + 8 * use_s);
+                            }
+                            if (4 * nq < nilim) {
 #pragma unroll
                                 for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -238,13 +291,17 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params
                             }
                         }
                     }
+                    if (++use_s == NSTAGE) {
+                        use_s = 0;
+                        ++use_k;
+                    }
                 }
                 // acc now holds S - K = -C
-                __syncthreads();                  // the stage area is free again
                 if ((DBG & 16) && tr_) tr_[4] = clock64();
 
                 if (it == 0) {
                     // ---- diagonal block: Cholesky of C[0:64, 0:64], one barrier per column ----
+                    __syncthreads();              // every warp is done with the stages Aw aliases
                     if (warp < 4) {
 #pragma unroll
                         for (int mi = 0; mi < 2; ++mi)
@@ -353,10 +410,8 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params
                 // tile's first chunks now so they land while the triangular solve runs
                 if (it + 1 < ntile) {
 #pragma unroll
-                    for (int s0 = 0; s0 < NSTAGE - 1; ++s0) {
-                        if (s0 < nk) load_stage(s0, s0, i0 + TM);
-                        cp_async_commit();
-                    }
+                    for (int s0 = 0; s0 < NSTAGE - 1; ++s0)
+                        if (s0 < nk) issue_chunk(s0, i0 + TM);
                 }
                 if ((DBG & 16) && tr_) tr_[5] = clock64();
                 if (it == 0 && warp < 4) continue;   // rows of the diagonal block are done
@@ -483,23 +538,8 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
         return MF_OK;
     }
     if (dbg) {
-#define DBG_ 1
-        if (dbg == 1) MF_LAUNCH(3, 2);
-#undef DBG_
-#define DBG_ 2
-        if (dbg == 2) MF_LAUNCH(3, 2);
-#undef DBG_
-#define DBG_ 3
-        if (dbg == 3) MF_LAUNCH(3, 2);
-#undef DBG_
-#define DBG_ 7
-        if (dbg == 7) MF_LAUNCH(3, 2);
-#undef DBG_
 #define DBG_ 8
         if (dbg == 8) MF_LAUNCH(3, 2);
-#undef DBG_
-#define DBG_ 4
-        if (dbg == 4) MF_LAUNCH(3, 2);
 #undef DBG_
         MF_CUDA_CHECK(h, cudaGetLastError());
         return MF_OK;
