@@ -24,6 +24,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum per matrix of order 1500, from the ncu capture of
+# one 296-matrix launch (profiles/r1_summary.md section 3)
+NCU_POTRF_BYTES_PER_EVAL = (34.417285e9 + 2.832004e9) / 296
+NCU_BUILD_BYTES_PER_EVAL = (0.018154e9 + 2.636645e9) / 296
+
 METRIC = "gp_loglike_evals_per_s"
 UNIT = "evals/s"
 
@@ -103,68 +108,100 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_evals(N, t, ys, errs, H, seconds, max_evals):
-    """The oracle's literal port of the reference's CPU path (17 N x N kernel
-    evaluations + scipy cho_factor/cho_solve per likelihood), timed on this
-    host's cores.  Returns (evals/s, evals done, values)."""
-    from oracle import gp_oracle as go
-    rv, rhk, bis = ys
-    e1, e2, e3 = errs
-    y = go.biggp_y(rv, rhk, bis)
-    go.biggp_loglike_literal("QuasiPeriodic", H[0], t, y, e1, e2, e3)      # BLAS thread start-up
-    vals = []
-    t0 = time.perf_counter()
-    while len(vals) < max_evals:
-        vals.append(go.biggp_loglike_literal("QuasiPeriodic", H[len(vals) % len(H)], t, y, e1, e2, e3))
-        if time.perf_counter() - t0 >= seconds:
-            break
-    dt = time.perf_counter() - t0
-    return len(vals) / dt, len(vals), np.array(vals)
+_WORK = {}
 
 
-def blas_threads():
+def _worker_init(N, seed):
+    """Pool worker: one BLAS thread each (the pool supplies the parallelism, as emcee's
+    `threads=` pool does in the reference, examples/BIGgp_mcmc.py:88)."""
+    from oracle import gp_oracle as go          # loads numpy's and scipy's BLAS ...
     try:
-        from threadpoolctl import threadpool_info
-        n = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
-        return max(n) if n else 1
+        from threadpoolctl import threadpool_limits
+        _WORK["limit"] = threadpool_limits(limits=1)      # ... which are then pinned to 1 thread
     except Exception:
-        return os.cpu_count() or 1
+        pass
+    t, (rv, rhk, bis), (e1, e2, e3) = go.synthetic_series(N, seed=seed)
+    _WORK.update(go=go, t=t, y=go.biggp_y(rv, rhk, bis), errs=(e1, e2, e3))
+
+
+def _worker_eval(rows):
+    go, t, y, (e1, e2, e3) = _WORK["go"], _WORK["t"], _WORK["y"], _WORK["errs"]
+    return [go.biggp_loglike_literal("QuasiPeriodic", a, t, y, e1, e2, e3) for a in rows]
+
+
+class CpuPort(object):
+    """The oracle's literal port of the reference's CPU path (17 N x N kernel-class
+    evaluations + scipy cho_factor / cho_solve per likelihood) on every host core: a pool
+    of single-threaded workers, one likelihood per task."""
+
+    def __init__(self, N, seed=1):
+        import multiprocessing as mp
+        self.cores = os.cpu_count() or 1
+        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_worker_init, initargs=(N, seed))
+
+    def evaluate(self, H):
+        chunks = [H[i:i + 1] for i in range(len(H))]
+        out = self.pool.map(_worker_eval, chunks)
+        return np.array([v for part in out for v in part])
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_port_evals(N, H, seconds, max_evals):
+    """Returns (evals/s, evals done, values, cores) for a bounded sample of H."""
+    port = CpuPort(N)
+    try:
+        port.evaluate(H[:port.cores])                      # worker start-up, not timed
+        t0 = time.perf_counter()
+        port.evaluate(H[:port.cores])
+        per_round = time.perf_counter() - t0
+        rounds = max(1, min(int(seconds / max(per_round, 1e-3)), max_evals // port.cores))
+        sample = H[:rounds * port.cores]
+        t0 = time.perf_counter()
+        vals = port.evaluate(sample)
+        dt = time.perf_counter() - t0
+        return len(vals) / dt, len(vals), vals, port.cores
+    finally:
+        port.close()
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path.  The
     reference is pure Python and /root/reference does not travel to the GPU box, so
-    this arm times the oracle's literal port of it (oracle/gp_oracle.py), all host
-    threads, a bounded sample of the same workload per step."""
+    this arm times the oracle's literal port of it (oracle/gp_oracle.py) on all host
+    cores, a bounded sample of the same workload per step."""
     if rank != 0:
         return
     N, t, ys, errs, H = workload(args, 0)
-    from oracle import gp_oracle as go
-    rv, rhk, bis = ys
-    e1, e2, e3 = errs
-    y = go.biggp_y(rv, rhk, bis)
-    sample = args.ref_sample
+    port = CpuPort(N)
+    try:
+        sample = args.ref_sample * port.cores
+        port.evaluate(H[:port.cores])                      # worker start-up
 
-    def step(k):
-        for i in range(sample):
-            go.biggp_loglike_literal("QuasiPeriodic", H[(k * sample + i) % len(H)], t, y, e1, e2, e3)
+        def step(k):
+            lo = (k * sample) % max(1, len(H) - sample)
+            port.evaluate(H[lo:lo + sample])
 
-    for k in range(args.warmup):
-        step(k)
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        step(args.warmup + k)
-    dt = time.perf_counter() - t0
+        for k in range(args.warmup):
+            step(k)
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            step(args.warmup + k)
+        dt = time.perf_counter() - t0
+        cores = port.cores
+    finally:
+        port.close()
     value = sample * args.steps / dt
-    cores = blas_threads()
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config_dict(args, world),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d of the %d hyper-parameter sets per step, numpy %s, "
-                                       "host cpu_count %s" % (sample, args.batch, np.__version__,
-                                                             os.cpu_count())},
+                             "sample": "%d of the %d hyper-parameter sets per step (pool of %d "
+                                       "single-threaded workers, numpy %s + scipy LAPACK)"
+                                       % (sample, args.batch, cores, np.__version__)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -314,13 +351,13 @@ def run_ours(args, rank, local_rank, world):
     cpu = None
     parity = None
     if world == 1 and not args.no_cpu_baseline:
-        rate, done, vals = cpu_port_evals(N, t, (rv, rhk, bis), (e1, e2, e3), H, args.cpu_seconds, 64)
+        rate, done, vals, cores = cpu_port_evals(N, H, args.cpu_seconds, 512)
         got = ll_d[:done].cpu().numpy()
         parity = float(np.max(np.abs(got - vals) / np.abs(vals)))
-        cpu = {"value": rate, "unit": UNIT, "cores": blas_threads(), "kind": "port",
-               "sample": "first %d of the %d hyper-parameter sets, oracle literal port "
-                         "(numpy %s + scipy LAPACK), host cpu_count %s"
-                         % (done, B, np.__version__, os.cpu_count())}
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "first %d of the %d hyper-parameter sets, oracle literal port of the "
+                         "reference (numpy %s + scipy LAPACK), pool of %d single-threaded workers"
+                         % (done, B, np.__version__, cores)}
 
     hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     try:
@@ -343,14 +380,18 @@ def run_ours(args, rank, local_rank, world):
         "gpu_launches": gpu_launches,
         "roofline": {"kernel": "mf_potrf_ll_kernel", "bound": "tensor", "achieved": potrf_tflops,
                      "peak": fp64_peak, "unit": "TFLOP/s", "frac": potrf_tflops / fp64_peak,
-                     "traffic": None,
+                     "traffic": NCU_POTRF_BYTES_PER_EVAL * per_launch / 1e9,
+                     "traffic_unit": "GB per launch (ncu dram read+write of a 296-matrix launch, "
+                                     "profiles/r1_summary.md, scaled to this launch)",
                      "peak_source": "FP64 is not in MEASURED_PEAKS.json: max of cuBLAS DGEMM 4096^3 "
                                     "(best of 5) and the DMMA register probe, both measured in this run",
                      "ms_per_launch": potrf_ms, "evals_per_launch": per_launch,
                      "flops_per_eval": flops_per_eval(n)},
         "roofline_build": {"kernel": "mf_cov_build_kernel", "bound": "hbm", "achieved": build_gbs,
                            "peak": hbm_peak, "unit": "GB/s", "frac": build_gbs / hbm_peak,
-                           "traffic": None, "peak_source": hbm_src, "ms_per_launch": build_ms,
+                           "traffic": NCU_BUILD_BYTES_PER_EVAL * per_launch / 1e9,
+                           "traffic_unit": "GB per launch (ncu, scaled as above)",
+                           "peak_source": hbm_src, "ms_per_launch": build_ms,
                            "bytes_per_eval": build_bytes_per_eval(n)},
         "fp64_peaks_measured": peaks,
         "cpu_baseline": cpu,
@@ -372,7 +413,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="hyper-parameter sets per GPU per step")
     ap.add_argument("--epochs", type=int, default=500, help="N; the matrix order is 3N")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--ref-sample", type=int, default=4, help="likelihoods per step of the reference arm")
+    ap.add_argument("--ref-sample", type=int, default=2,
+                    help="likelihoods per host core per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
