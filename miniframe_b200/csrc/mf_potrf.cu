@@ -39,7 +39,7 @@ constexpr int AW_LD = 65;
 // a 16-byte fragment load of rows g, g+1 then covers one 128-byte line, conflict-free.
 constexpr int SZ_LD = 36 * 64 * 8;
 constexpr int SZ_DINV = 8 * 64 * 8;                  // minus-inverses of the 8 diagonal 8x8 blocks
-constexpr int SZ_COL = 2 * 72 * 8;                   // double-buffered scaled pivot column + status
+constexpr int SZ_COL = (2 * 136 + 128) * 8;          // double-buffered pivot column (v, v/d, status), pivots, 1/sqrt
 constexpr int SZ_RED = 64 * 8;                       // reduction scratch + 2 x NSTAGE mbarriers
 constexpr int smem_bytes(int nstage) { return nstage * STAGE_BYTES + SZ_LD + SZ_DINV + SZ_COL + SZ_RED; }
 static_assert(NB * AW_LD * 8 <= 2 * STAGE_BYTES, "potf2 staging array must fit in the stage area");
@@ -87,7 +87,7 @@ __device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
 
 // DBG (timing experiments only): 8 = skip the contraction loop (results are garbage),
 // 16 = record per-tile phase timestamps of the first matrix of every CTA
-template <int NSTAGE, int MINB, int DBG>
+template <int NSTAGE, int MINB, int DBG, int VAR>
 __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params p) {
     constexpr int OFF_LD = NSTAGE * STAGE_BYTES;
     constexpr int OFF_DINV = OFF_LD + SZ_LD;
@@ -322,31 +322,50 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params
                     for (int cb = 0; cb < 4; ++cb) {
                         for (int cl = 0; cl < 16; ++cl) {
                             const int c = 16 * cb + cl;
-                            if (c >= nv) break;
-                            double* col = colbuf + (c & 1) * 72;
+                            if (c >= nv || (DBG & 32)) break;
+                            double* col = colbuf + (c & 1) * 136;
                             if (tc == cl) {
                                 // the 16 threads that own column c sit in one half-warp; lane cl of
                                 // it owns the pivot
                                 const double d = __shfl_sync(0xffffu << (16 * (lane >> 4)), e[cb][cb], (lane & 16) + cl);
                                 const bool bad = !DBG && !(d > 0.0);   // LAPACK dpotrf pivot test
-                                const double rs = bad ? 0.0 : rsqrt(d);
-                                if (tr == cl) col[64] = bad ? -1.0 : 1.0;
+                                if (VAR == 0) {
+                                    const double rs = bad ? 0.0 : rsqrt(d);
+                                    if (tr == cl) col[128] = bad ? -1.0 : 1.0;
 #pragma unroll
-                                for (int a = 0; a < 4; ++a) {
-                                    const int r = tr + 16 * a;
-                                    const double v = (r > c) ? e[a][cb] * rs : (r == c ? d * rs : 0.0);
-                                    col[r] = v;
-                                    if ((r >> 3) >= (c >> 3)) Ld[ldblk(r >> 3, c >> 3) + (r & 7) * 8 + (c & 7)] = v;
+                                    for (int a = 0; a < 4; ++a) {
+                                        const int r = tr + 16 * a;
+                                        const double v = (r > c) ? e[a][cb] * rs : (r == c ? d * rs : 0.0);
+                                        col[r] = v;
+                                        col[64 + r] = v;
+                                        if ((r >> 3) >= (c >> 3)) Ld[ldblk(r >> 3, c >> 3) + (r & 7) * 8 + (c & 7)] = v;
+                                    }
+                                } else {
+                                    // L D L^T recurrence: only a reciprocal sits on the pivot chain, the
+                                    // 1/sqrt(d) scaling of the columns is applied after the last pivot
+                                    const double inv = bad ? 0.0 : __drcp_rn(d);
+                                    if (tr == cl) {
+                                        col[128] = bad ? -1.0 : 1.0;
+                                        colbuf[272 + c] = d;
+                                    }
+#pragma unroll
+                                    for (int a = 0; a < 4; ++a) {
+                                        const int r = tr + 16 * a;
+                                        const double v = (r > c) ? e[a][cb] : (r == c ? d : 0.0);
+                                        col[r] = v;
+                                        col[64 + r] = v * inv;
+                                        if ((r >> 3) >= (c >> 3)) Ld[ldblk(r >> 3, c >> 3) + (r & 7) * 8 + (c & 7)] = v;
+                                    }
                                 }
                             }
                             __syncthreads();
-                            if (col[64] < 0.0) {
+                            if (col[128] < 0.0) {
                                 fail = j0 + c + 1;
                                 break;
                             }
                             double lr[4], lk[4];
 #pragma unroll
-                            for (int a = 0; a < 4; ++a) lr[a] = col[tr + 16 * a];
+                            for (int a = 0; a < 4; ++a) lr[a] = col[64 + tr + 16 * a];
 #pragma unroll
                             for (int b = 0; b < 4; ++b) lk[b] = col[tc + 16 * b];
 #pragma unroll
@@ -359,6 +378,20 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params
                         if (fail) break;
                     }
                     if (fail) break;
+                    if (VAR == 1) {
+                        // scale column c by 1/sqrt(d_c): L = V D^-1/2, L_cc = d_c / sqrt(d_c)
+                        __syncthreads();
+                        if (tid < 64) colbuf[336 + tid] = (tid < nv) ? rsqrt(colbuf[272 + tid]) : 1.0;
+                        __syncthreads();
+                        for (int idx = tid; idx < 36 * 64; idx += THREADS) {
+                            const int blkid = idx >> 6, rr = (idx >> 3) & 7, cc = idx & 7;
+                            int bi = 0;
+                            while ((bi + 1) * (bi + 2) / 2 <= blkid) ++bi;
+                            const int bj = blkid - bi * (bi + 1) / 2;
+                            const int c = 8 * bj + cc;
+                            if (c < nv && 8 * bi + rr >= c) Ld[idx] *= colbuf[336 + c];
+                        }
+                    }
                     // columns beyond the matrix order: identity, keeps the 8x8 inverses finite
                     if (tid < 64)
                         for (int c = nv; c < NB; ++c)
@@ -422,6 +455,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params
                 // column groups (still negated) absorb +X L^T ----
 #pragma unroll
                 for (int nb = 0; nb < 8; ++nb) {
+                    if (DBG & 64) break;
                     const double2 dv = *reinterpret_cast<const double2*>(Dinv + nb * 64 + g * 8 + 2 * t);
 #pragma unroll
                     for (int mi = 0; mi < 2; ++mi) {
@@ -446,7 +480,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params
 #pragma unroll
                 for (int mi = 0; mi < 2; ++mi) {
                     const int row = wrow0 + 8 * mi + g;
-                    if (row <= n) {
+                    if (row <= n && !(DBG & 128)) {
 #pragma unroll
                         for (int ni = 0; ni < 8; ++ni) {
                             const int col = j0 + 8 * ni + 2 * t;
@@ -512,11 +546,12 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
     cudaStream_t st = (cudaStream_t)stream;
 #define MF_LAUNCH(NS, MB)                                                                          \
     do {                                                                                           \
-        MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<NS, MB, DBG_>,                \
+        MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<NS, MB, DBG_, VAR_>,                \
                                               cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                               pf::smem_bytes(NS)));                                \
-        pf::mf_potrf_ll_kernel<NS, MB, DBG_><<<grid, pf::THREADS, pf::smem_bytes(NS), st>>>(p);    \
+        pf::mf_potrf_ll_kernel<NS, MB, DBG_, VAR_><<<grid, pf::THREADS, pf::smem_bytes(NS), st>>>(p);    \
     } while (0)
+#define VAR_ 0
     const char* ed = getenv("MF_DBG");
     const int dbg = ed ? atoi(ed) : 0;
     p.trace = nullptr;
@@ -541,11 +576,33 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
 #define DBG_ 8
         if (dbg == 8) MF_LAUNCH(3, 2);
 #undef DBG_
+#define DBG_ 32
+        if (dbg == 32) MF_LAUNCH(3, 2);
+#undef DBG_
+#define DBG_ 64
+        if (dbg == 64) MF_LAUNCH(3, 2);
+#undef DBG_
+#define DBG_ 96
+        if (dbg == 96) MF_LAUNCH(3, 2);
+#undef DBG_
+#define DBG_ 128
+        if (dbg == 128) MF_LAUNCH(3, 2);
+#undef DBG_
+#define DBG_ 224
+        if (dbg == 224) MF_LAUNCH(3, 2);
+#undef DBG_
         MF_CUDA_CHECK(h, cudaGetLastError());
         return MF_OK;
     }
 #define DBG_ 0
-    if (per_sm >= 2) {
+    const char* ev = getenv("MF_VARIANT");
+    if (ev && atoi(ev) == 1 && per_sm >= 2) {
+#undef VAR_
+#define VAR_ 1
+        MF_LAUNCH(3, 2);
+#undef VAR_
+#define VAR_ 0
+    } else if (per_sm >= 2) {
         MF_LAUNCH(3, 2);
     } else {
         switch (nstage) {
@@ -557,6 +614,7 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
     }
 #undef MF_LAUNCH
 #undef DBG_
+#undef VAR_
     MF_CUDA_CHECK(h, cudaGetLastError());
     return MF_OK;
 }
