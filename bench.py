@@ -56,7 +56,7 @@ def config_dict(args, world):
             "matrix_order": 3 * args.epochs, "per_gpu_batch": args.batch,
             "global_batch": args.batch * world, "sharding": "batch over ranks, allgather of ll",
             "l2_policy": "inputs larger than L2 (%.1f GB of matrices per step per GPU)"
-                         % (args.batch * (3 * args.epochs + 1) * ((3 * args.epochs + 15) // 16 * 16) * 8 / 1e9)}
+                         % (args.batch * ((3 * args.epochs + 8) // 8 * 8) * ((3 * args.epochs + 15) // 16 * 16) * 8 / 1e9)}
 
 
 class ClockSampler(object):

@@ -21,7 +21,8 @@
  *     produces (BIGgp.py:310-311, SMALLgp.py:274-276).
  *
  * Workspace matrix layout ("packed lower + residual row")
- *   One matrix of order n = n_series * n_epochs occupies (n + 1) rows of
+ *   One matrix of order n = n_series * n_epochs occupies n + 1 rows (allocated as
+ *   8 * ceil((n + 1) / 8) rows: the factorisation moves 8-row groups) of
  *   ld = mf_ld(n) doubles, row-major.  Rows 0..n-1 hold the covariance matrix
  *   (the lower triangle is what the factorisation reads and overwrites with
  *   L, K = L L^T); row n receives z = L^-1 r, the forward-substituted
@@ -102,7 +103,7 @@ int  mf_device_info(mf_handle_t h, int* sm_count, int* cc_major, int* cc_minor);
 
 /* layout helpers (host arithmetic only) */
 int64_t mf_ld(int n);               /* leading dimension in doubles, multiple of 16 */
-int64_t mf_matrix_stride(int n);    /* (n + 1) * mf_ld(n) doubles */
+int64_t mf_matrix_stride(int n);    /* 8 * ceil((n + 1) / 8) * mf_ld(n) doubles */
 size_t  mf_workspace_bytes(int batch, int n);
 
 /*

@@ -78,12 +78,12 @@ class Engine(object):
 
     # -- kernels -----------------------------------------------------------
     def build_cov(self, prob, t, diag_add, hyper, extra, full=True):
-        """Returns the (B, n+1, ld) workspace tensor; [:, :n, :n] is K."""
+        """Returns the (B, rows, ld) workspace tensor (rows = stride / ld >= n + 1); [:, :n, :n] is K."""
         torch = _torch()
         B = hyper.shape[0]
         n = prob.n_series * prob.n_epochs
         ld, stride = self.ld(n), self.matrix_stride(n)
-        K = torch.zeros((B, n + 1, ld), dtype=torch.float64, device=self.device)
+        K = torch.zeros((B, stride // ld, ld), dtype=torch.float64, device=self.device)
         st = self.lib.mf_build_cov(self.handle, ctypes.byref(prob), B, self.ptr(t), self.ptr(diag_add),
                                    self.ptr(hyper), self.ptr(extra), 1 if full else 0,
                                    self.ptr(K), ld, stride, self.stream())

@@ -64,7 +64,7 @@ extern "C" int mf_device_info(mf_handle_t h, int* sm_count, int* cc_major, int* 
 }
 
 extern "C" int64_t mf_ld(int n) { return mf_ld_of(n); }
-extern "C" int64_t mf_matrix_stride(int n) { return ((int64_t)n + 1) * mf_ld_of(n); }
+extern "C" int64_t mf_matrix_stride(int n) { return mf_rows_of(n) * mf_ld_of(n); }
 extern "C" size_t mf_workspace_bytes(int batch, int n) {
     return (size_t)batch * (size_t)mf_matrix_stride(n) * sizeof(double);
 }

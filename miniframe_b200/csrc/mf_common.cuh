@@ -33,6 +33,9 @@ struct mf_handle_s {
 
 // ---- layout -----------------------------------------------------------------
 __host__ __device__ inline int64_t mf_ld_of(int n) { return ((int64_t)n + 15) / 16 * 16; }
+// rows allocated per matrix: the n covariance rows + the z row, rounded up to whole 8-row groups
+// (the TMA box of the factorisation kernel moves 8-row groups)
+__host__ __device__ inline int64_t mf_rows_of(int n) { return ((int64_t)n + 1 + 7) / 8 * 8; }
 
 // ---- device primitives --------------------------------------------------------
 #ifdef __CUDACC__

@@ -9,10 +9,12 @@
 //     one CTA are hidden behind the other CTA's tensor-core work;
 //   * LEFT-looking by 64-wide block columns: tile C(128 x 64) = K - L_left L_top^T
 //     is a dense contraction over the already-final columns, accumulated in
-//     registers with mma.sync m8n8k4 f64 (SASS DMMA.8x8x4) from a cp.async
-//     double-buffered, XOR-swizzled shared-memory pipeline.  Every tile of K is
-//     read once and every tile of L written once (HBM traffic ~ n^3/(6*64)*8 B
-//     per matrix, arithmetic intensity 16 flop/B);
+//     registers with mma.sync m8n8k4 f64 (SASS DMMA.8x8x4).  The operands stream
+//     through a 3-stage shared-memory ring fed by TMA (cp.async.bulk.tensor.5d,
+//     SASS UTMALDG.5D, 128-byte hardware swizzle) issued by one elected thread and
+//     synchronised with mbarriers only - no CTA-wide barrier inside the loop.
+//     Every tile of K is read once and every tile of L written once (HBM traffic
+//     ~ n^3/(6*64)*8 B per matrix, arithmetic intensity 16 flop/B);
 //   * each warp owns 16 complete rows (16 x 64 accumulators), so the triangular
 //     solve against the diagonal block runs entirely in registers on the tensor
 //     cores: the C-fragment layout (row g, columns 2t, 2t+1) is reused directly as
@@ -21,6 +23,7 @@
 //   * the residual vector rides along as row n of the matrix: its row of L is
 //     z = L^-1 r, so the forward substitution costs one extra row in the last row
 //     tile, and -1/2 z.z - sum(log L_ii) - n/2 log(2 pi) falls out at the end.
+#include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -39,13 +42,16 @@ constexpr int AW_LD = 65;
 // a 16-byte fragment load of rows g, g+1 then covers one 128-byte line, conflict-free.
 constexpr int SZ_LD = 36 * 64 * 8;
 constexpr int SZ_DINV = 8 * 64 * 8;                  // minus-inverses of the 8 diagonal 8x8 blocks
-constexpr int SZ_COL = (2 * 136 + 128) * 8;          // double-buffered pivot column (v, v/d, status), pivots, 1/sqrt
+constexpr int SZ_COL = 2 * 72 * 8;                   // double-buffered pivot column: 64 values + status word
 constexpr int SZ_RED = 64 * 8;                       // reduction scratch + 2 x NSTAGE mbarriers
-constexpr int smem_bytes(int nstage) { return nstage * STAGE_BYTES + SZ_LD + SZ_DINV + SZ_COL + SZ_RED; }
+constexpr int smem_bytes(int nstage) { return nstage * STAGE_BYTES + SZ_LD + SZ_DINV + SZ_COL + SZ_RED + 1024; }
 static_assert(NB * AW_LD * 8 <= 2 * STAGE_BYTES, "potf2 staging array must fit in the stage area");
 // 3 stages: 97,792 B, two CTAs per SM
 
 struct Params {
+    // 5-D tensor map over the chunk of matrices for the TMA-fed ring:
+    // {column, row 0/2/4/6 of an 8-row group, row parity, 8-row group, matrix}
+    alignas(64) CUtensorMap tmap;
     int batch;
     int n;
     double* K;
@@ -80,20 +86,34 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         ::"r"(bar), "r"(parity)
         : "memory");
 }
-// arrive on `bar` once all cp.async copies this thread has issued so far have landed
-__device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// one 64-row x 16-column box of matrix `mat`, rows 8 * blk8 .., columns c0 ..; lands 128B-swizzled
+__device__ __forceinline__ void tma_box(uint32_t dst, const CUtensorMap* tm, int c0, int blk8, int mat, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(0), "r"(0), "r"(blk8), "r"(mat), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void fence_async_proxy() {
+    asm volatile("fence.proxy.async;" ::: "memory");
 }
 
-// DBG (timing experiments only): 8 = skip the contraction loop (results are garbage),
-// 16 = record per-tile phase timestamps of the first matrix of every CTA
-template <int NSTAGE, int MINB, int DBG, int VAR>
-__global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params p) {
+// DBG (timing experiments only, results are garbage except for 16): bit mask,
+//   8 = consume the ring without computing, 16 = record per-tile phase timestamps of the
+//   first matrix of every CTA, 32 = skip the diagonal-block factorisation, 64 = skip the
+//   triangular solve, 128 = skip the stores of L
+template <int NSTAGE, int MINB, int DBG>
+__global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid_constant__ Params p) {
     constexpr int OFF_LD = NSTAGE * STAGE_BYTES;
     constexpr int OFF_DINV = OFF_LD + SZ_LD;
     constexpr int OFF_COL = OFF_DINV + SZ_DINV;
     constexpr int OFF_RED = OFF_COL + SZ_COL;
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // 128B-swizzled TMA boxes need 1 KB alignment: align by hand, one spare KB is allocated
+    unsigned char* const smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     double* const Aw = reinterpret_cast<double*>(smem);                 // aliases the stages
     double* const Ld = reinterpret_cast<double*>(smem + OFF_LD);
     double* const Dinv = reinterpret_cast<double*>(smem + OFF_DINV);
@@ -106,25 +126,25 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params
     const int n = p.n;
     const int64_t ld = p.ld;
 
-    // cp.async mapping: 8 consecutive threads move one 128-byte row of a stage
-    const int lrow = tid >> 3, lch = tid & 7;
-    const uint32_t ldst = stage_u32 + lrow * 128 + ((lch ^ ((lrow & 1) << 2)) << 4);
-    // fragment address inside a stage: 16-byte chunk (4h + t) of row r, swizzled by row parity
-    const int fswz = (g & 1) << 2;
+    // A stage holds 192 rows (128 of the row tile, 64 of the block column's own rows) of 16
+    // doubles, 128 bytes each.  The tensor map delivers the rows of every 8-row group in the
+    // order 0,2,4,6,1,3,5,7 and the hardware 128B swizzle XORs the 16-byte chunk index with the
+    // row position mod 8, so the 16-byte fragment loads of a quarter warp (lane groups g, g+1:
+    // positions 4 apart, chunk index t) hit eight different 16-byte bank groups: conflict-free.
+    const int gp = (g >> 1) | ((g & 1) << 2);      // position of row g inside its 8-row group
     // potf2 ownership: rows tr + 16a, columns tc + 16b (a, b = 0..3) live in registers
     const int tr = tid & 15, tc = tid >> 4;
 
     // producer/consumer ring over the stages, no CTA-wide barrier in the contraction loop:
-    //   full[s]  - 256 arrivals, one per thread, raised by the copy engine when that thread's
-    //              cp.async copies into stage s have landed;
-    //   empty[s] - 8 arrivals, one per warp, after the warp's last fragment load from stage s.
+    //   full[s]  - one arrival (the producer's expect_tx) + the 24,576 bytes the TMA delivers;
+    //   empty[s] - 8 arrivals, one per warp, once the warp has consumed its fragments of stage s.
     // Chunks are numbered over the whole kernel lifetime (gfill issued, guse consumed):
     // chunk c lives in stage c % NSTAGE and is that stage's (c / NSTAGE)-th use.
     const uint32_t bar_full = smem_u32(smem + OFF_RED + 256);
     const uint32_t bar_empty = bar_full + 8 * NSTAGE;
     if (tid == 0) {
         for (int s0 = 0; s0 < NSTAGE; ++s0) {
-            mbar_init(bar_full + 8 * s0, THREADS);
+            mbar_init(bar_full + 8 * s0, 1);
             mbar_init(bar_empty + 8 * s0, THREADS / 32);
         }
     }
@@ -138,6 +158,13 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params
         double logdet = 0.0;          // meaningful in warp 0 only
         int fail = 0;
         const int ncb = (n + NB - 1) / NB;
+        {
+            // the TMA boxes move whole 8-row groups: rows n+1 .. 8*ceil((n+1)/8)-1 must read as zero
+            const int64_t pad = (mf_rows_of(n) - (n + 1)) * ld;
+            double* zp = Kb + (size_t)(n + 1) * ld;
+            for (int64_t k = tid; k < pad; k += THREADS) zp[k] = 0.0;
+            fence_async_proxy();
+        }
 
         for (int jb = 0; jb < ncb && !fail; ++jb) {
             const int j0 = jb * NB;
@@ -149,6 +176,12 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params
             // memory before anyone prefetches them (the first chunks are issued ahead of
             // the first barrier of the contraction loop); also fences the stage area
             __syncthreads();
+            // The rows of L this block column streams were written through the generic proxy by
+            // all threads (ordered by the barrier above); the thread that issues the TMA loads
+            // must itself order them before its async-proxy reads.  One fence per block column is
+            // enough: nothing read inside a block column is written inside it.  (Measured: with
+            // writer-side fences only, ~13 % of the matrices of a full wave come out wrong.)
+            if (tid == 0) fence_async_proxy();
 
             for (int it = 0; it < ntile; ++it) {
                 const int i0 = j0 + it * TM;
@@ -168,17 +201,18 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params
                 if (it == 0 && warp < 4) nilim = min(nilim, 2 * warp + 2);
 
                 auto issue_chunk = [&](int kc, int r0) {
-                    // wait until every warp has released the previous use of this stage
-                    if (fill_k > 0) mbar_wait(bar_empty + 8 * fill_s, (fill_k - 1) & 1);
-                    const double* src_col = Kb + (size_t)kc * KC + lch * 2;
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) {
-                        const int grow = (q < 4) ? (r0 + lrow + 32 * q) : (j0 + lrow + 32 * (q - 4));
-                        const bool ok = grow <= n;
-                        const double* src = ok ? src_col + (size_t)grow * ld : Kb;
-                        cp_async16(ldst + fill_s * STAGE_BYTES + q * (32 * 128), src, ok ? 16 : 0);
+                    // one elected thread feeds the ring: wait until every warp has released the
+                    // previous use of the stage, then three 64-row TMA boxes (rows beyond the
+                    // allocation are zero-filled by the hardware)
+                    if (tid == 0) {
+                        if (fill_k > 0) mbar_wait(bar_empty + 8 * fill_s, (fill_k - 1) & 1);
+                        const uint32_t bar = bar_full + 8 * fill_s;
+                        const uint32_t dst = stage_u32 + fill_s * STAGE_BYTES;
+                        mbar_expect_tx(bar, STAGE_BYTES);
+                        tma_box(dst, &p.tmap, kc * KC, r0 >> 3, mat, bar);
+                        tma_box(dst + 8192, &p.tmap, kc * KC, (r0 >> 3) + 8, mat, bar);
+                        tma_box(dst + 16384, &p.tmap, kc * KC, j0 >> 3, mat, bar);
                     }
-                    cp_async_mbar_arrive(bar_full + 8 * fill_s);
                     if (++fill_s == NSTAGE) {
                         fill_s = 0;
                         ++fill_k;
@@ -259,23 +293,18 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params
                             // the tensor pipe already has work queued while the copies go out
                             if (kc + NSTAGE - 1 < nk) issue_chunk(kc + NSTAGE - 1, i0);
                         }
-                        const int choff = ((4 * h + t) ^ fswz) << 4;
+                        const int choff = ((4 * h + t) ^ gp) << 4;
                         double2 a[2];
 #pragma unroll
                         for (int mi = 0; mi < 2; ++mi)
-                            a[mi] = *reinterpret_cast<const double2*>(sb + (16 * warp + 8 * mi + g) * 128 + choff);
+                            a[mi] = *reinterpret_cast<const double2*>(sb + (16 * warp + 8 * mi + gp) * 128 + choff);
 #pragma unroll
                         for (int nq = 0; nq < 2; ++nq) {
                             double2 b[4];
                             if (4 * nq < nilim) {
 #pragma unroll
                                 for (int u = 0; u < 4; ++u)
-                                    b[u] = *reinterpret_cast<const double2*>(sb + (TM + 8 * (4 * nq + u) + g) * 128 + choff);
-                            }
-                            if (h == 1 && nq == 1) {
-                                // last fragment load of this chunk: hand the stage back
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive(bar_empty + 8 * use_s);
+                                    b[u] = *reinterpret_cast<const double2*>(sb + (TM + 8 * (4 * nq + u) + gp) * 128 + choff);
                             }
                             if (4 * nq < nilim) {
 #pragma unroll
@@ -283,6 +312,17 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params
 #pragma unroll
                                     for (int mi = 0; mi < 2; ++mi)
                                         dmma884(acc[mi][4 * nq + u][0], acc[mi][4 * nq + u][1], a[mi].x, b[u].x);
+                            }
+                            if (h == 1 && nq == 1) {
+                                // Hand the stage back.  The arrival must not overtake the fragment
+                                // loads: it is placed after tensor-core instructions that consume every
+                                // register those loads fill, so the loads have completed by then (an
+                                // arrive right after the loads let the TMA overwrite a stage that was
+                                // still being read).
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(bar_empty + 8 * use_s);
+                            }
+                            if (4 * nq < nilim) {
 #pragma unroll
                                 for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -311,6 +351,8 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params
                                 d[0] = flip(acc[mi][ni][0]);
                                 d[1] = flip(acc[mi][ni][1]);
                             }
+                        // these generic-proxy writes land in memory the TMA (async proxy) refills later
+                        fence_async_proxy();
                     }
                     __syncthreads();
                     double e[4][4];
@@ -323,49 +365,30 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params
                         for (int cl = 0; cl < 16; ++cl) {
                             const int c = 16 * cb + cl;
                             if (c >= nv || (DBG & 32)) break;
-                            double* col = colbuf + (c & 1) * 136;
+                            double* col = colbuf + (c & 1) * 72;
                             if (tc == cl) {
                                 // the 16 threads that own column c sit in one half-warp; lane cl of
                                 // it owns the pivot
                                 const double d = __shfl_sync(0xffffu << (16 * (lane >> 4)), e[cb][cb], (lane & 16) + cl);
                                 const bool bad = !DBG && !(d > 0.0);   // LAPACK dpotrf pivot test
-                                if (VAR == 0) {
-                                    const double rs = bad ? 0.0 : rsqrt(d);
-                                    if (tr == cl) col[128] = bad ? -1.0 : 1.0;
+                                const double rs = bad ? 0.0 : rsqrt(d);
+                                if (tr == cl) col[64] = bad ? -1.0 : 1.0;
 #pragma unroll
-                                    for (int a = 0; a < 4; ++a) {
-                                        const int r = tr + 16 * a;
-                                        const double v = (r > c) ? e[a][cb] * rs : (r == c ? d * rs : 0.0);
-                                        col[r] = v;
-                                        col[64 + r] = v;
-                                        if ((r >> 3) >= (c >> 3)) Ld[ldblk(r >> 3, c >> 3) + (r & 7) * 8 + (c & 7)] = v;
-                                    }
-                                } else {
-                                    // L D L^T recurrence: only a reciprocal sits on the pivot chain, the
-                                    // 1/sqrt(d) scaling of the columns is applied after the last pivot
-                                    const double inv = bad ? 0.0 : __drcp_rn(d);
-                                    if (tr == cl) {
-                                        col[128] = bad ? -1.0 : 1.0;
-                                        colbuf[272 + c] = d;
-                                    }
-#pragma unroll
-                                    for (int a = 0; a < 4; ++a) {
-                                        const int r = tr + 16 * a;
-                                        const double v = (r > c) ? e[a][cb] : (r == c ? d : 0.0);
-                                        col[r] = v;
-                                        col[64 + r] = v * inv;
-                                        if ((r >> 3) >= (c >> 3)) Ld[ldblk(r >> 3, c >> 3) + (r & 7) * 8 + (c & 7)] = v;
-                                    }
+                                for (int a = 0; a < 4; ++a) {
+                                    const int r = tr + 16 * a;
+                                    const double v = (r > c) ? e[a][cb] * rs : (r == c ? d * rs : 0.0);
+                                    col[r] = v;
+                                    if ((r >> 3) >= (c >> 3)) Ld[ldblk(r >> 3, c >> 3) + (r & 7) * 8 + (c & 7)] = v;
                                 }
                             }
                             __syncthreads();
-                            if (col[128] < 0.0) {
+                            if (col[64] < 0.0) {
                                 fail = j0 + c + 1;
                                 break;
                             }
                             double lr[4], lk[4];
 #pragma unroll
-                            for (int a = 0; a < 4; ++a) lr[a] = col[64 + tr + 16 * a];
+                            for (int a = 0; a < 4; ++a) lr[a] = col[tr + 16 * a];
 #pragma unroll
                             for (int b = 0; b < 4; ++b) lk[b] = col[tc + 16 * b];
 #pragma unroll
@@ -378,20 +401,6 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params
                         if (fail) break;
                     }
                     if (fail) break;
-                    if (VAR == 1) {
-                        // scale column c by 1/sqrt(d_c): L = V D^-1/2, L_cc = d_c / sqrt(d_c)
-                        __syncthreads();
-                        if (tid < 64) colbuf[336 + tid] = (tid < nv) ? rsqrt(colbuf[272 + tid]) : 1.0;
-                        __syncthreads();
-                        for (int idx = tid; idx < 36 * 64; idx += THREADS) {
-                            const int blkid = idx >> 6, rr = (idx >> 3) & 7, cc = idx & 7;
-                            int bi = 0;
-                            while ((bi + 1) * (bi + 2) / 2 <= blkid) ++bi;
-                            const int bj = blkid - bi * (bi + 1) / 2;
-                            const int c = 8 * bj + cc;
-                            if (c < nv && 8 * bi + rr >= c) Ld[idx] *= colbuf[336 + c];
-                        }
-                    }
                     // columns beyond the matrix order: identity, keeps the 8x8 inverses finite
                     if (tid < 64)
                         for (int c = nv; c < NB; ++c)
@@ -437,6 +446,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params
                                 dst[0] = v.x;
                         }
                     }
+                    fence_async_proxy();          // L_jj -> async proxy
                     __syncthreads();
                 }
                 // the stage area is idle from here to the next contraction loop: start the next
@@ -492,6 +502,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const Params
                         }
                     }
                 }
+                fence_async_proxy();              // X -> async proxy
             }
         }
 
@@ -524,9 +535,35 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
     if (!K || !ll || !info) MF_FAIL(h, MF_ERR_INVALID, "null pointer");
     if (batch <= 0 || n <= 0) MF_FAIL(h, MF_ERR_INVALID, "batch and n must be positive");
     if (ld < n || (ld % 16) != 0) MF_FAIL(h, MF_ERR_INVALID, "ld must be a multiple of 16 and >= n");
-    if (stride < (int64_t)(n + 1) * ld) MF_FAIL(h, MF_ERR_INVALID, "stride must cover n + 1 rows");
+    if (stride < mf_rows_of(n) * ld)
+        MF_FAIL(h, MF_ERR_INVALID, "stride must cover 8 * ceil((n + 1) / 8) rows (mf_matrix_stride)");
     if (((uintptr_t)K & 15) != 0) MF_FAIL(h, MF_ERR_INVALID, "K must be 16-byte aligned");
     pf::Params p;
+    {
+        // tensor map for the TMA ring; cuTensorMapEncodeTiled comes from the driver through
+        // the runtime's entry-point query (no link-time dependency on libcuda)
+        typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                      CUtensorMapFloatOOBfill);
+        static encode_fn encode = nullptr;
+        if (!encode) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            MF_CUDA_CHECK(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+            if (!fn || qres != cudaDriverEntryPointSuccess) MF_FAIL(h, MF_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+            encode = (encode_fn)fn;
+        }
+        const cuuint64_t gdim[5] = {(cuuint64_t)ld, 4, 2, (cuuint64_t)(mf_rows_of(n) / 8), (cuuint64_t)batch};
+        const cuuint64_t gstr[4] = {(cuuint64_t)(2 * ld * 8), (cuuint64_t)(ld * 8), (cuuint64_t)(8 * ld * 8),
+                                    (cuuint64_t)(stride * 8)};
+        const cuuint32_t box[5] = {16, 4, 2, 8, 1};
+        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        CUresult cr = encode(&p.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, K, gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) MF_FAIL(h, MF_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)cr);
+    }
     p.batch = batch;
     p.n = n;
     p.K = K;
@@ -537,21 +574,18 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
     p.ll = ll;
     p.info = info;
     p.sm_count = h->sm_count;
-    const char* es = getenv("MF_SLOTS_PER_SM");
-    const char* en = getenv("MF_NSTAGE");
-    const int per_sm = es ? atoi(es) : 2;
-    const int nstage = en ? atoi(en) : 3;
-    const int slots = per_sm * h->sm_count;
+    const int slots = 2 * h->sm_count;      // two resident CTAs per SM (registers and shared memory)
     const int grid = batch < slots ? batch : slots;
     cudaStream_t st = (cudaStream_t)stream;
-#define MF_LAUNCH(NS, MB)                                                                          \
+#define MF_LAUNCH(DBG_)                                                                            \
     do {                                                                                           \
-        MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<NS, MB, DBG_, VAR_>,                \
+        MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<3, 2, DBG_>,                  \
                                               cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                                              pf::smem_bytes(NS)));                                \
-        pf::mf_potrf_ll_kernel<NS, MB, DBG_, VAR_><<<grid, pf::THREADS, pf::smem_bytes(NS), st>>>(p);    \
+                                              pf::smem_bytes(3)));                                 \
+        pf::mf_potrf_ll_kernel<3, 2, DBG_><<<grid, pf::THREADS, pf::smem_bytes(3), st>>>(p);       \
     } while (0)
-#define VAR_ 0
+    // MF_DBG selects one of the timing-experiment instantiations (scripts/gpu_sweep.sh,
+    // scripts/trace_run.py); results of those launches are not valid likelihoods
     const char* ed = getenv("MF_DBG");
     const int dbg = ed ? atoi(ed) : 0;
     p.trace = nullptr;
@@ -559,9 +593,7 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
         const size_t words = (size_t)grid * 200 * 8;
         MF_CUDA_CHECK(h, cudaMalloc(&p.trace, words * 8));
         MF_CUDA_CHECK(h, cudaMemsetAsync(p.trace, 0, words * 8, st));
-#define DBG_ 16
-        MF_LAUNCH(3, 2);
-#undef DBG_
+        MF_LAUNCH(16);
         MF_CUDA_CHECK(h, cudaStreamSynchronize(st));
         long long* host = (long long*)malloc(words * 8);
         MF_CUDA_CHECK(h, cudaMemcpy(host, p.trace, words * 8, cudaMemcpyDeviceToHost));
@@ -572,49 +604,16 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
         cudaFree(p.trace);
         return MF_OK;
     }
-    if (dbg) {
-#define DBG_ 8
-        if (dbg == 8) MF_LAUNCH(3, 2);
-#undef DBG_
-#define DBG_ 32
-        if (dbg == 32) MF_LAUNCH(3, 2);
-#undef DBG_
-#define DBG_ 64
-        if (dbg == 64) MF_LAUNCH(3, 2);
-#undef DBG_
-#define DBG_ 96
-        if (dbg == 96) MF_LAUNCH(3, 2);
-#undef DBG_
-#define DBG_ 128
-        if (dbg == 128) MF_LAUNCH(3, 2);
-#undef DBG_
-#define DBG_ 224
-        if (dbg == 224) MF_LAUNCH(3, 2);
-#undef DBG_
-        MF_CUDA_CHECK(h, cudaGetLastError());
-        return MF_OK;
-    }
-#define DBG_ 0
-    const char* ev = getenv("MF_VARIANT");
-    if (ev && atoi(ev) == 1 && per_sm >= 2) {
-#undef VAR_
-#define VAR_ 1
-        MF_LAUNCH(3, 2);
-#undef VAR_
-#define VAR_ 0
-    } else if (per_sm >= 2) {
-        MF_LAUNCH(3, 2);
-    } else {
-        switch (nstage) {
-            case 4: MF_LAUNCH(4, 1); break;
-            case 6: MF_LAUNCH(6, 1); break;
-            case 8: MF_LAUNCH(8, 1); break;
-            default: MF_LAUNCH(3, 1); break;
-        }
+    switch (dbg) {
+        case 8: MF_LAUNCH(8); break;
+        case 32: MF_LAUNCH(32); break;
+        case 64: MF_LAUNCH(64); break;
+        case 96: MF_LAUNCH(96); break;
+        case 128: MF_LAUNCH(128); break;
+        case 224: MF_LAUNCH(224); break;
+        default: MF_LAUNCH(0); break;
     }
 #undef MF_LAUNCH
-#undef DBG_
-#undef VAR_
     MF_CUDA_CHECK(h, cudaGetLastError());
     return MF_OK;
 }

@@ -33,8 +33,8 @@ def test_library_exports_every_declared_symbol():
     assert lib.mf_status_string(0) == b"ok"
     # layout helpers are host arithmetic
     assert lib.mf_ld(1500) == 1504 and lib.mf_ld(1504) == 1504 and lib.mf_ld(1) == 16
-    assert lib.mf_matrix_stride(1500) == 1501 * 1504
-    assert lib.mf_workspace_bytes(4, 600) == 4 * 601 * 608 * 8
+    assert lib.mf_matrix_stride(1500) == 1504 * 1504 and lib.mf_matrix_stride(7) == 8 * 16
+    assert lib.mf_workspace_bytes(4, 600) == 4 * 608 * 608 * 8
 
 
 def test_no_cpu_fallback():
