@@ -104,7 +104,8 @@ __device__ __forceinline__ void fence_async_proxy() {
 // DBG (timing experiments only, results are garbage except for 16): bit mask,
 //   8 = consume the ring without computing, 16 = record per-tile phase timestamps of the
 //   first matrix of every CTA, 32 = skip the diagonal-block factorisation, 64 = skip the
-//   triangular solve, 128 = skip the stores of L
+//   triangular solve, 128 = skip the stores of L, 256 = stream the operands of every matrix from
+//   the first four (L2-resident)
 template <int NSTAGE, int MINB, int DBG>
 __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid_constant__ Params p) {
     constexpr int OFF_LD = NSTAGE * STAGE_BYTES;
@@ -135,22 +136,25 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
     // potf2 ownership: rows tr + 16a, columns tc + 16b (a, b = 0..3) live in registers
     const int tr = tid & 15, tc = tid >> 4;
 
-    // producer/consumer ring over the stages, no CTA-wide barrier in the contraction loop:
-    //   full[s]  - one arrival (the producer's expect_tx) + the 24,576 bytes the TMA delivers;
-    //   empty[s] - 8 arrivals, one per warp, once the warp has consumed its fragments of stage s.
-    // Chunks are numbered over the whole kernel lifetime (gfill issued, guse consumed):
-    // chunk c lives in stage c % NSTAGE and is that stage's (c / NSTAGE)-th use.
+    // Operand ring over the stages, no CTA-wide barrier and no producer wait in the
+    // contraction loop:
+    //   full[s]     - mbarrier: one arrival (the issuer's expect_tx) + the 24,576 bytes the TMA
+    //                 delivers; every warp waits on it before reading stage s;
+    //   released[s] - plain counter: a warp adds one once it has consumed its fragments of
+    //                 stage s; the warp that brings it to a multiple of 8 knows the stage is free
+    //                 and refills it itself, NSTAGE chunks ahead.
+    // Chunks are numbered over the whole kernel lifetime: chunk c lives in stage c % NSTAGE and
+    // is that stage's (c / NSTAGE)-th use (use_s, use_k: the next chunk this warp consumes).
     const uint32_t bar_full = smem_u32(smem + OFF_RED + 256);
-    const uint32_t bar_empty = bar_full + 8 * NSTAGE;
+    int* const released = reinterpret_cast<int*>(smem + OFF_RED + 256 + 8 * NSTAGE);
     if (tid == 0) {
         for (int s0 = 0; s0 < NSTAGE; ++s0) {
             mbar_init(bar_full + 8 * s0, 1);
-            mbar_init(bar_empty + 8 * s0, THREADS / 32);
+            released[s0] = 0;
         }
     }
     __syncthreads();
-    uint32_t fill_s = 0, fill_k = 0;      // stage / use count of the next chunk to issue
-    uint32_t use_s = 0, use_k = 0;        // ... of the next chunk to consume
+    uint32_t use_s = 0, use_k = 0;
 
     for (int mat = blockIdx.x; mat < p.batch; mat += gridDim.x) {
         double* const Kb = p.K + (size_t)mat * p.stride;
@@ -177,11 +181,12 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
             // the first barrier of the contraction loop); also fences the stage area
             __syncthreads();
             // The rows of L this block column streams were written through the generic proxy by
-            // all threads (ordered by the barrier above); the thread that issues the TMA loads
-            // must itself order them before its async-proxy reads.  One fence per block column is
-            // enough: nothing read inside a block column is written inside it.  (Measured: with
-            // writer-side fences only, ~13 % of the matrices of a full wave come out wrong.)
-            if (tid == 0) fence_async_proxy();
+            // all threads (ordered by the barrier above); a thread that issues TMA loads must
+            // itself order them before its async-proxy reads, and any warp's lane 0 may be the
+            // issuer.  One fence per block column is enough: nothing read inside a block column
+            // is written inside it.  (Measured: with writer-side fences only, ~13 % of the
+            // matrices of a full wave come out wrong.)
+            fence_async_proxy();
 
             for (int it = 0; it < ntile; ++it) {
                 const int i0 = j0 + it * TM;
@@ -200,31 +205,45 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 int nilim = (wrow0 > n) ? 0 : nicols;
                 if (it == 0 && warp < 4) nilim = min(nilim, 2 * warp + 2);
 
-                auto issue_chunk = [&](int kc, int r0) {
-                    // one elected thread feeds the ring: wait until every warp has released the
-                    // previous use of the stage, then three 64-row TMA boxes (rows beyond the
-                    // allocation are zero-filled by the hardware)
-                    if (tid == 0) {
-                        if (fill_k > 0) mbar_wait(bar_empty + 8 * fill_s, (fill_k - 1) & 1);
-                        const uint32_t bar = bar_full + 8 * fill_s;
-                        const uint32_t dst = stage_u32 + fill_s * STAGE_BYTES;
-                        mbar_expect_tx(bar, STAGE_BYTES);
-                        tma_box(dst, &p.tmap, kc * KC, r0 >> 3, mat, bar);
-                        tma_box(dst + 8192, &p.tmap, kc * KC, (r0 >> 3) + 8, mat, bar);
-                        tma_box(dst + 16384, &p.tmap, kc * KC, j0 >> 3, mat, bar);
-                    }
-                    if (++fill_s == NSTAGE) {
-                        fill_s = 0;
-                        ++fill_k;
+                // put chunk kc of the row tile at r0 into stage st: three 64-row TMA boxes, issued by
+                // one thread (rows beyond the allocation are zero-filled by the hardware)
+                auto tma_chunk = [&](uint32_t st, int kc, int r0) {
+                    const uint32_t bar = bar_full + 8 * st;
+                    const uint32_t dst = stage_u32 + st * STAGE_BYTES;
+                    mbar_expect_tx(bar, STAGE_BYTES);
+                    const int lmat = (DBG & 256) ? (mat & 3) : mat;
+                    tma_box(dst, &p.tmap, kc * KC, r0 >> 3, lmat, bar);
+                    tma_box(dst + 8192, &p.tmap, kc * KC, (r0 >> 3) + 8, lmat, bar);
+                    tma_box(dst + 16384, &p.tmap, kc * KC, j0 >> 3, lmat, bar);
+                };
+                // The warp has consumed chunk kc (stage use_s).  The LAST of the eight warps to
+                // say so refills the stage at once with the chunk NSTAGE further on - of this tile,
+                // else of the next tile of the block column (not from the diagonal tile, whose
+                // factorisation scratch aliases the stages).  Nobody ever waits for a free stage.
+                auto release_stage = [&](int kc) {
+                    if (DBG & 512) return;
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int old = atomicAdd(released + use_s, 1);
+                        if ((old & 7) == 7) {
+                            int tk = kc + NSTAGE, r0 = i0;
+                            bool go = true;
+                            if (tk >= nk) {
+                                tk -= nk;
+                                r0 = i0 + TM;
+                                go = (it > 0) && (it + 1 < ntile);
+                            }
+                            if (go) tma_chunk(use_s, tk, r0);
+                        }
                     }
                 };
 
-                // pipeline prologue: up to NSTAGE - 1 chunks in flight; for every tile but the
-                // first of a block column it was issued before the previous tile's triangular solve
-                if (it == 0) {
+                // pipeline prologue of a block column: fill the whole ring (every later tile finds
+                // its first chunks already issued by the tail of its predecessor, see below)
+                if (it == 0 && tid == 0 && !(DBG & 512)) {
 #pragma unroll
-                    for (int s0 = 0; s0 < NSTAGE - 1; ++s0)
-                        if (s0 < nk) issue_chunk(s0, i0);
+                    for (int s0 = 0; s0 < NSTAGE; ++s0)
+                        if (s0 < nk) tma_chunk((use_s + s0) % NSTAGE, s0, i0);
                 }
                 // pull the NEXT tile of K (same block column, else the head of the next one)
                 // into L2 while this tile is being contracted: one 512-byte row per thread
@@ -278,33 +297,26 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 for (int kc = 0; kc < nk; ++kc) {
                     if (DBG & 8) {          // timing experiment: consume the ring without computing
                         mbar_wait(bar_full + 8 * use_s, use_k & 1);
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_empty + 8 * use_s);
-                        if (kc + NSTAGE - 1 < nk) issue_chunk(kc + NSTAGE - 1, i0);
+                        release_stage(kc);
                         if (++use_s == NSTAGE) { use_s = 0; ++use_k; }
                         continue;
                     }
-                    mbar_wait(bar_full + 8 * use_s, use_k & 1);      // chunk kc has landed
+                    if (!(DBG & 512)) mbar_wait(bar_full + 8 * use_s, use_k & 1);      // chunk kc has landed
                     const unsigned char* sb = smem + use_s * STAGE_BYTES;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        if (h == 1) {
-                            // refill the ring two chunks ahead; issued between the two halves so
-                            // the tensor pipe already has work queued while the copies go out
-                            if (kc + NSTAGE - 1 < nk) issue_chunk(kc + NSTAGE - 1, i0);
-                        }
                         const int choff = ((4 * h + t) ^ gp) << 4;
                         double2 a[2];
 #pragma unroll
                         for (int mi = 0; mi < 2; ++mi)
-                            a[mi] = *reinterpret_cast<const double2*>(sb + (16 * warp + 8 * mi + gp) * 128 + choff);
+                            a[mi] = (DBG & 1024) ? make_double2(1.0 + mi, 0.5) : *reinterpret_cast<const double2*>(sb + (16 * warp + 8 * mi + gp) * 128 + choff);
 #pragma unroll
                         for (int nq = 0; nq < 2; ++nq) {
                             double2 b[4];
                             if (4 * nq < nilim) {
 #pragma unroll
                                 for (int u = 0; u < 4; ++u)
-                                    b[u] = *reinterpret_cast<const double2*>(sb + (TM + 8 * (4 * nq + u) + gp) * 128 + choff);
+                                    b[u] = (DBG & 1024) ? make_double2(1.0 + u, 0.25) : *reinterpret_cast<const double2*>(sb + (TM + 8 * (4 * nq + u) + gp) * 128 + choff);
                             }
                             if (4 * nq < nilim) {
 #pragma unroll
@@ -319,8 +331,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                                 // register those loads fill, so the loads have completed by then (an
                                 // arrive right after the loads let the TMA overwrite a stage that was
                                 // still being read).
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive(bar_empty + 8 * use_s);
+                                release_stage(kc);
                             }
                             if (4 * nq < nilim) {
 #pragma unroll
@@ -451,10 +462,11 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 }
                 // the stage area is idle from here to the next contraction loop: start the next
                 // tile's first chunks now so they land while the triangular solve runs
-                if (it + 1 < ntile) {
+                // (the tail of every other tile has already refilled the ring for its successor)
+                if (it == 0 && ntile > 1 && tid == 0 && !(DBG & 512)) {
 #pragma unroll
-                    for (int s0 = 0; s0 < NSTAGE - 1; ++s0)
-                        if (s0 < nk) issue_chunk(s0, i0 + TM);
+                    for (int s0 = 0; s0 < NSTAGE; ++s0)
+                        if (s0 < nk) tma_chunk((use_s + s0) % NSTAGE, s0, i0 + TM);
                 }
                 if ((DBG & 16) && tr_) tr_[5] = clock64();
                 if (it == 0 && warp < 4) continue;   // rows of the diagonal block are done
@@ -604,6 +616,14 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
         cudaFree(p.trace);
         return MF_OK;
     }
+    if (getenv("MF_NSTAGE") && atoi(getenv("MF_NSTAGE")) == 2) {
+        MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<2, 2, 224>, cudaFuncAttributeMaxDynamicSharedMemorySize, pf::smem_bytes(3)));
+        MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<2, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, pf::smem_bytes(3)));
+        if (dbg == 224) pf::mf_potrf_ll_kernel<2, 2, 224><<<grid, pf::THREADS, pf::smem_bytes(3), st>>>(p);
+        else pf::mf_potrf_ll_kernel<2, 2, 0><<<grid, pf::THREADS, pf::smem_bytes(3), st>>>(p);
+        MF_CUDA_CHECK(h, cudaGetLastError());
+        return MF_OK;
+    }
     switch (dbg) {
         case 8: MF_LAUNCH(8); break;
         case 32: MF_LAUNCH(32); break;
@@ -611,6 +631,12 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
         case 96: MF_LAUNCH(96); break;
         case 128: MF_LAUNCH(128); break;
         case 224: MF_LAUNCH(224); break;
+        case 256: MF_LAUNCH(256); break;
+        case 288: MF_LAUNCH(288); break;
+        case 480: MF_LAUNCH(480); break;
+        case 736: MF_LAUNCH(736); break;
+        case 1248: MF_LAUNCH(1248); break;
+        case 1760: MF_LAUNCH(1760); break;
         default: MF_LAUNCH(0); break;
     }
 #undef MF_LAUNCH
