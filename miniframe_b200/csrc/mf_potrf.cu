@@ -104,8 +104,7 @@ __device__ __forceinline__ void fence_async_proxy() {
 // DBG (timing experiments only, results are garbage except for 16): bit mask,
 //   8 = consume the ring without computing, 16 = record per-tile phase timestamps of the
 //   first matrix of every CTA, 32 = skip the diagonal-block factorisation, 64 = skip the
-//   triangular solve, 128 = skip the stores of L, 256 = stream the operands of every matrix from
-//   the first four (L2-resident)
+//   triangular solve, 256 = stream the operands of every matrix from the first four (L2-resident)
 template <int NSTAGE, int MINB, int DBG>
 __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid_constant__ Params p) {
     constexpr int OFF_LD = NSTAGE * STAGE_BYTES;
@@ -135,6 +134,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
     const int gp = (g >> 1) | ((g & 1) << 2);      // position of row g inside its 8-row group
     // potf2 ownership: rows tr + 16a, columns tc + 16b (a, b = 0..3) live in registers
     const int tr = tid & 15, tc = tid >> 4;
+    const int tbw = warp < 4 ? warp : 11 - warp;   // 8-row block of this warp inside each 64-row half tile
 
     // Operand ring over the stages, no CTA-wide barrier and no producer wait in the
     // contraction loop:
@@ -190,7 +190,12 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
 
             for (int it = 0; it < ntile; ++it) {
                 const int i0 = j0 + it * TM;
-                const int wrow0 = i0 + 16 * warp;              // first row this warp owns
+                // Rows of the tile are dealt to the warps in 8-row fragments: fragment mi of warp w
+                // is rows 8 tb(w) + 64 mi .. + 7 with tb = 0,1,2,3,7,6,5,4.  Warps w and w + 4 share
+                // an SM sub-partition, so every sub-partition gets the same tensor work both in the
+                // diagonal tile (triangle blocks s and 7 - s: s + 1 and 8 - s column groups) and in
+                // the ragged last tile of a block column (valid fragments spread round-robin).
+                const int wrow0 = i0 + 8 * tbw;                // first row of fragment 0; fragment 1 is 64 below
                 long long* tr_ = nullptr;
                 if ((DBG & 16) && mat == (int)blockIdx.x && tid == 0) {
                     int tix = 0;
@@ -202,8 +207,9 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 }
                 // 8-column groups this warp has to produce: none if its rows lie beyond the
                 // residual row, only the lower triangle inside the diagonal block
-                int nilim = (wrow0 > n) ? 0 : nicols;
-                if (it == 0 && warp < 4) nilim = min(nilim, 2 * warp + 2);
+                int nil0 = (wrow0 > n) ? 0 : nicols;
+                const int nil1 = (wrow0 + 64 > n) ? 0 : nicols;
+                if (it == 0) nil0 = min(nil0, tbw + 1);
 
                 // put chunk kc of the row tile at r0 into stage st: three 64-row TMA boxes, issued by
                 // one thread (rows beyond the allocation are zero-filled by the hardware)
@@ -221,7 +227,6 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 // else of the next tile of the block column (not from the diagonal tile, whose
                 // factorisation scratch aliases the stages).  Nobody ever waits for a free stage.
                 auto release_stage = [&](int kc) {
-                    if (DBG & 512) return;
                     __syncwarp();
                     if (lane == 0) {
                         const int old = atomicAdd(released + use_s, 1);
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
 
                 // pipeline prologue of a block column: fill the whole ring (every later tile finds
                 // its first chunks already issued by the tail of its predecessor, see below)
-                if (it == 0 && tid == 0 && !(DBG & 512)) {
+                if (it == 0 && tid == 0) {
 #pragma unroll
                     for (int s0 = 0; s0 < NSTAGE; ++s0)
                         if (s0 < nk) tma_chunk((use_s + s0) % NSTAGE, s0, i0);
@@ -263,7 +268,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 if (interior) {
 #pragma unroll
                     for (int mi = 0; mi < 2; ++mi) {
-                        const double* src = Kb + (size_t)(wrow0 + 8 * mi + g) * ld + j0 + 2 * t;
+                        const double* src = Kb + (size_t)(wrow0 + 64 * mi + g) * ld + j0 + 2 * t;
 #pragma unroll
                         for (int ni = 0; ni < 8; ++ni) {
                             const double2 v = *reinterpret_cast<const double2*>(src + 8 * ni);
@@ -274,7 +279,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 } else {
 #pragma unroll
                     for (int mi = 0; mi < 2; ++mi) {
-                        const int row = wrow0 + 8 * mi + g;
+                        const int row = wrow0 + 64 * mi + g;
 #pragma unroll
                         for (int ni = 0; ni < 8; ++ni) {
                             const int col = j0 + 8 * ni + 2 * t;
@@ -301,7 +306,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                         if (++use_s == NSTAGE) { use_s = 0; ++use_k; }
                         continue;
                     }
-                    if (!(DBG & 512)) mbar_wait(bar_full + 8 * use_s, use_k & 1);      // chunk kc has landed
+                    mbar_wait(bar_full + 8 * use_s, use_k & 1);      // chunk kc has landed
                     const unsigned char* sb = smem + use_s * STAGE_BYTES;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -309,21 +314,30 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                         double2 a[2];
 #pragma unroll
                         for (int mi = 0; mi < 2; ++mi)
-                            a[mi] = (DBG & 1024) ? make_double2(1.0 + mi, 0.5) : *reinterpret_cast<const double2*>(sb + (16 * warp + 8 * mi + gp) * 128 + choff);
+                            a[mi] = *reinterpret_cast<const double2*>(sb + (8 * tbw + 64 * mi + gp) * 128 + choff);
 #pragma unroll
                         for (int nq = 0; nq < 2; ++nq) {
+                            // warp-uniform block-level branches (not per-instruction predicates): they
+                            // keep ptxas from hoisting the next group's loads into this group
                             double2 b[4];
-                            if (4 * nq < nilim) {
+                            const bool d0 = 4 * nq < nil0, d1 = 4 * nq < nil1;
+                            if (d0 || d1) {
 #pragma unroll
                                 for (int u = 0; u < 4; ++u)
-                                    b[u] = (DBG & 1024) ? make_double2(1.0 + u, 0.25) : *reinterpret_cast<const double2*>(sb + (TM + 8 * (4 * nq + u) + gp) * 128 + choff);
+                                    b[u] = *reinterpret_cast<const double2*>(sb + (TM + 8 * (4 * nq + u) + gp) * 128 + choff);
                             }
-                            if (4 * nq < nilim) {
+                            if (d0 && d1) {
 #pragma unroll
                                 for (int u = 0; u < 4; ++u)
 #pragma unroll
                                     for (int mi = 0; mi < 2; ++mi)
                                         dmma884(acc[mi][4 * nq + u][0], acc[mi][4 * nq + u][1], a[mi].x, b[u].x);
+                            } else if (d0) {
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) dmma884(acc[0][4 * nq + u][0], acc[0][4 * nq + u][1], a[0].x, b[u].x);
+                            } else if (d1) {
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) dmma884(acc[1][4 * nq + u][0], acc[1][4 * nq + u][1], a[1].x, b[u].x);
                             }
                             if (h == 1 && nq == 1) {
                                 // Hand the stage back.  The arrival must not overtake the fragment
@@ -333,12 +347,18 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                                 // still being read).
                                 release_stage(kc);
                             }
-                            if (4 * nq < nilim) {
+                            if (d0 && d1) {
 #pragma unroll
                                 for (int u = 0; u < 4; ++u)
 #pragma unroll
                                     for (int mi = 0; mi < 2; ++mi)
                                         dmma884(acc[mi][4 * nq + u][0], acc[mi][4 * nq + u][1], a[mi].y, b[u].y);
+                            } else if (d0) {
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) dmma884(acc[0][4 * nq + u][0], acc[0][4 * nq + u][1], a[0].y, b[u].y);
+                            } else if (d1) {
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) dmma884(acc[1][4 * nq + u][0], acc[1][4 * nq + u][1], a[1].y, b[u].y);
                             }
                         }
                     }
@@ -353,18 +373,15 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 if (it == 0) {
                     // ---- diagonal block: Cholesky of C[0:64, 0:64], one barrier per column ----
                     __syncthreads();              // every warp is done with the stages Aw aliases
-                    if (warp < 4) {
+                    // fragment 0 of every warp is its 8-row block of the diagonal block
 #pragma unroll
-                        for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-                            for (int ni = 0; ni < 8; ++ni) {
-                                double* d = Aw + (16 * warp + 8 * mi + g) * AW_LD + 8 * ni + 2 * t;
-                                d[0] = flip(acc[mi][ni][0]);
-                                d[1] = flip(acc[mi][ni][1]);
-                            }
-                        // these generic-proxy writes land in memory the TMA (async proxy) refills later
-                        fence_async_proxy();
+                    for (int ni = 0; ni < 8; ++ni) {
+                        double* d = Aw + (8 * tbw + g) * AW_LD + 8 * ni + 2 * t;
+                        d[0] = flip(acc[0][ni][0]);
+                        d[1] = flip(acc[0][ni][1]);
                     }
+                    // these generic-proxy writes land in memory the TMA (async proxy) refills later
+                    fence_async_proxy();
                     __syncthreads();
                     double e[4][4];
 #pragma unroll
@@ -463,14 +480,15 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 // the stage area is idle from here to the next contraction loop: start the next
                 // tile's first chunks now so they land while the triangular solve runs
                 // (the tail of every other tile has already refilled the ring for its successor)
-                if (it == 0 && ntile > 1 && tid == 0 && !(DBG & 512)) {
+                if (it == 0 && ntile > 1 && tid == 0) {
 #pragma unroll
                     for (int s0 = 0; s0 < NSTAGE; ++s0)
                         if (s0 < nk) tma_chunk((use_s + s0) % NSTAGE, s0, i0 + TM);
                 }
                 if ((DBG & 16) && tr_) tr_[5] = clock64();
-                if (it == 0 && warp < 4) continue;   // rows of the diagonal block are done
-                if (wrow0 > n) continue;             // nothing real in this warp's rows
+                // fragments that still need the solve: real rows, not part of the diagonal block
+                const bool act[2] = {it > 0 && wrow0 <= n, wrow0 + 64 <= n};
+                if (!act[0] && !act[1]) continue;
 
                 // ---- X = C L_jj^-T on the tensor cores, 8-column blocks, in registers.
                 // acc holds -C; Dinv holds -inv(L_bb), so x = acc Dinv^T = +X, and the later
@@ -481,6 +499,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                     const double2 dv = *reinterpret_cast<const double2*>(Dinv + nb * 64 + g * 8 + 2 * t);
 #pragma unroll
                     for (int mi = 0; mi < 2; ++mi) {
+                        if (!act[mi]) continue;
                         double x0 = 0.0, x1 = 0.0;
                         dmma884(x0, x1, acc[mi][nb][0], dv.x);
                         dmma884(x0, x1, acc[mi][nb][1], dv.y);
@@ -492,6 +511,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                         const double2 lv = *reinterpret_cast<const double2*>(Ld + ldblk(nb2, nb) + g * 8 + 2 * t);
 #pragma unroll
                         for (int mi = 0; mi < 2; ++mi) {
+                            if (!act[mi]) continue;
                             dmma884(acc[mi][nb2][0], acc[mi][nb2][1], acc[mi][nb][0], lv.x);
                             dmma884(acc[mi][nb2][0], acc[mi][nb2][1], acc[mi][nb][1], lv.y);
                         }
@@ -501,8 +521,8 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 // ---- rows of L (and z) are final: write them once ----
 #pragma unroll
                 for (int mi = 0; mi < 2; ++mi) {
-                    const int row = wrow0 + 8 * mi + g;
-                    if (row <= n && !(DBG & 128)) {
+                    const int row = wrow0 + 64 * mi + g;
+                    if (act[mi] && row <= n) {
 #pragma unroll
                         for (int ni = 0; ni < 8; ++ni) {
                             const int col = j0 + 8 * ni + 2 * t;
@@ -616,27 +636,13 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
         cudaFree(p.trace);
         return MF_OK;
     }
-    if (getenv("MF_NSTAGE") && atoi(getenv("MF_NSTAGE")) == 2) {
-        MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<2, 2, 224>, cudaFuncAttributeMaxDynamicSharedMemorySize, pf::smem_bytes(3)));
-        MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<2, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, pf::smem_bytes(3)));
-        if (dbg == 224) pf::mf_potrf_ll_kernel<2, 2, 224><<<grid, pf::THREADS, pf::smem_bytes(3), st>>>(p);
-        else pf::mf_potrf_ll_kernel<2, 2, 0><<<grid, pf::THREADS, pf::smem_bytes(3), st>>>(p);
-        MF_CUDA_CHECK(h, cudaGetLastError());
-        return MF_OK;
-    }
     switch (dbg) {
         case 8: MF_LAUNCH(8); break;
         case 32: MF_LAUNCH(32); break;
         case 64: MF_LAUNCH(64); break;
         case 96: MF_LAUNCH(96); break;
-        case 128: MF_LAUNCH(128); break;
-        case 224: MF_LAUNCH(224); break;
         case 256: MF_LAUNCH(256); break;
         case 288: MF_LAUNCH(288); break;
-        case 480: MF_LAUNCH(480); break;
-        case 736: MF_LAUNCH(736); break;
-        case 1248: MF_LAUNCH(1248); break;
-        case 1760: MF_LAUNCH(1760); break;
         default: MF_LAUNCH(0); break;
     }
 #undef MF_LAUNCH
