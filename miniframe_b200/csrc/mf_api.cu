@@ -44,11 +44,24 @@ extern "C" int mf_create(mf_handle_t* out, int device) {
         delete h;
         return MF_ERR_CUDA;
     }
+    h->coop_groups = 2 * h->sm_count;
+    h->coop_sync = nullptr;
+    h->coop_dinv = nullptr;
+    if (cudaMalloc(&h->coop_sync, (size_t)h->coop_groups * 8 * sizeof(unsigned)) != cudaSuccess ||
+        cudaMalloc(&h->coop_dinv, (size_t)h->coop_groups * 512 * sizeof(double)) != cudaSuccess) {
+        cudaFree(h->coop_sync);
+        delete h;
+        return MF_ERR_CUDA;
+    }
     *out = h;
     return MF_OK;
 }
 
 extern "C" int mf_destroy(mf_handle_t h) {
+    if (h) {
+        cudaFree(h->coop_sync);
+        cudaFree(h->coop_dinv);
+    }
     delete h;
     return MF_OK;
 }

@@ -12,6 +12,11 @@ struct mf_handle_s {
     int sm_count;
     int cc_major, cc_minor;
     size_t smem_optin;
+    // scratch of the cooperative (several CTAs per matrix) factorisation, allocated once by
+    // mf_create: per group 8 synchronisation words and the 8 negated 8x8 inverses (512 doubles)
+    unsigned* coop_sync;
+    double* coop_dinv;
+    int coop_groups;
     char err[512];
 };
 

@@ -62,6 +62,11 @@ struct Params {
     double* ll;
     int32_t* info;
     int sm_count;
+    // cooperative variant (COOP): `group` CTAs share one matrix; 8 words + 512 doubles per group
+    int group;
+    unsigned* sync;       // [0] barrier arrivals, [1] diagonal-block sequence number, [2] failed matrix
+                          // ordinal + 1, [3] info of the failure, [4..7] two log-det accumulators
+    double* dinv;
     long long* trace;     // DBG & 16: per-tile phase timestamps of the first matrix of each CTA
 };
 
@@ -97,6 +102,14 @@ __device__ __forceinline__ void tma_box(uint32_t dst, const CUtensorMap* tm, int
         ::"r"(dst), "l"(tm), "r"(c0), "r"(0), "r"(0), "r"(blk8), "r"(mat), "r"(bar)
         : "memory");
 }
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void fence_async_proxy() {
     asm volatile("fence.proxy.async;" ::: "memory");
 }
@@ -105,7 +118,15 @@ __device__ __forceinline__ void fence_async_proxy() {
 //   8 = consume the ring without computing, 16 = record per-tile phase timestamps of the
 //   first matrix of every CTA, 32 = skip the diagonal-block factorisation, 64 = skip the
 //   triangular solve, 256 = stream the operands of every matrix from the first four (L2-resident)
-template <int NSTAGE, int MINB, int DBG>
+// COOP = 1: `p.group` CTAs (all co-resident: cooperative launch) factorise one matrix together.
+// Inside a block column the row tiles are independent once L_jj is known, so tile `it` goes to
+// CTA (jb + it) mod G of the group; the owner of the diagonal tile publishes L_jj (it is in the
+// matrix) and the 8x8 inverses through global memory and a sequence number, the others contract
+// their tiles first and pick L_jj up just before their triangular solve.  One group barrier
+// (atomic counter, release/acquire) per block column orders the rows written by the other CTAs
+// before the TMA loads of the next block column.  Few large matrices (n = 30000, B = 1 or 64) or
+// a small ensemble then fill the GPU instead of one SM per matrix.
+template <int NSTAGE, int MINB, int DBG, int COOP>
 __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid_constant__ Params p) {
     constexpr int OFF_LD = NSTAGE * STAGE_BYTES;
     constexpr int OFF_DINV = OFF_LD + SZ_LD;
@@ -156,7 +177,27 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
     __syncthreads();
     uint32_t use_s = 0, use_k = 0;
 
-    for (int mat = blockIdx.x; mat < p.batch; mat += gridDim.x) {
+    const int G = COOP ? p.group : 1;
+    const int grp = COOP ? (int)blockIdx.x / G : (int)blockIdx.x;
+    const int rank = COOP ? (int)blockIdx.x % G : 0;
+    const int ngroups = COOP ? (int)gridDim.x / G : (int)gridDim.x;
+    unsigned* const gsync = COOP ? p.sync + 8 * grp : nullptr;
+    double* const gdinv = COOP ? p.dinv + 512 * grp : nullptr;
+    unsigned bar_target = 0;          // arrivals that complete the next group barrier
+    unsigned ordinal = 0;             // matrices this group has started before this one
+    auto group_barrier = [&]() {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(gsync, 1u);
+            bar_target += (unsigned)G;
+            while ((int)(ld_acquire(gsync) - bar_target) < 0) {
+            }
+        }
+        __syncthreads();
+    };
+
+    for (int mat = grp; mat < p.batch; mat += ngroups, ++ordinal) {
         double* const Kb = p.K + (size_t)mat * p.stride;
         const double* const rb = p.resid ? p.resid + (size_t)mat * p.resid_stride : nullptr;
         double logdet = 0.0;          // meaningful in warp 0 only
@@ -170,7 +211,14 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
             fence_async_proxy();
         }
 
-        for (int jb = 0; jb < ncb && !fail; ++jb) {
+        for (int jb = 0; jb < ncb; ++jb) {
+            if (COOP && jb > 0) {
+                // rows of the previous block column, written by every CTA of the group, are visible
+                // from here on; a failed pivot is learnt here by the CTAs that did not meet it
+                group_barrier();
+                if (ld_acquire(gsync + 2) == ordinal + 1) fail = (int)ld_acquire(gsync + 3);
+            }
+            if (fail) break;
             const int j0 = jb * NB;
             const int nv = min(NB, n - j0);
             const int ntile = (n + 1 - j0 + TM - 1) / TM;
@@ -188,7 +236,10 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
             // matrices of a full wave come out wrong.)
             fence_async_proxy();
 
-            for (int it = 0; it < ntile; ++it) {
+            const int it_first = COOP ? (rank - jb % G + G) % G : 0;
+            const unsigned seq = ordinal * (unsigned)ncb + (unsigned)jb + 1u;
+            bool have_L = !COOP;
+            for (int it = it_first; it < ntile; it += G) {
                 const int i0 = j0 + it * TM;
                 // Rows of the tile are dealt to the warps in 8-row fragments: fragment mi of warp w
                 // is rows 8 tb(w) + 64 mi .. + 7 with tb = 0,1,2,3,7,6,5,4.  Warps w and w + 4 share
@@ -235,8 +286,8 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                             bool go = true;
                             if (tk >= nk) {
                                 tk -= nk;
-                                r0 = i0 + TM;
-                                go = (it > 0) && (it + 1 < ntile);
+                                r0 = i0 + G * TM;
+                                go = (it > 0) && (it + G < ntile);
                             }
                             if (go) tma_chunk(use_s, tk, r0);
                         }
@@ -245,7 +296,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
 
                 // pipeline prologue of a block column: fill the whole ring (every later tile finds
                 // its first chunks already issued by the tail of its predecessor, see below)
-                if (it == 0 && tid == 0) {
+                if (it == it_first && tid == 0) {
 #pragma unroll
                     for (int s0 = 0; s0 < NSTAGE; ++s0)
                         if (s0 < nk) tma_chunk((use_s + s0) % NSTAGE, s0, i0);
@@ -253,9 +304,9 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 // pull the NEXT tile of K (same block column, else the head of the next one)
                 // into L2 while this tile is being contracted: one 512-byte row per thread
                 if (tid < TM) {
-                    const bool same = it + 1 < ntile;
+                    const bool same = it + G < ntile;
                     const int pj = same ? j0 : j0 + NB;
-                    const int prow = (same ? i0 + TM : j0 + NB) + tid;
+                    const int prow = (same ? i0 + G * TM : j0 + NB) + tid;
                     if (prow < n && pj < n) {
                         const unsigned bytes = (unsigned)min(NB, (int)ld - pj) * 8u;
                         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Kb + (size_t)prow * ld + pj), "r"(bytes) : "memory");
@@ -428,7 +479,15 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                         }
                         if (fail) break;
                     }
-                    if (fail) break;
+                    if (fail) {
+                        if (COOP && tid == 0) {       // tell the group, then release whoever waits for L_jj
+                            gsync[3] = (unsigned)fail;
+                            __threadfence();
+                            st_release(gsync + 2, ordinal + 1);
+                            st_release(gsync + 1, seq);
+                        }
+                        break;
+                    }
                     // columns beyond the matrix order: identity, keeps the 8x8 inverses finite
                     if (tid < 64)
                         for (int c = nv; c < NB; ++c)
@@ -476,14 +535,57 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                     }
                     fence_async_proxy();          // L_jj -> async proxy
                     __syncthreads();
+                    if (COOP) {
+                        // publish: L_jj is in the matrix, the inverses go to the group's scratch
+                        gdinv[tid] = Dinv[tid];
+                        gdinv[tid + THREADS] = Dinv[tid + THREADS];
+                        __threadfence();
+                        __syncthreads();
+                        if (tid == 0) st_release(gsync + 1, seq);
+                    }
+                    have_L = true;
+                } else if (COOP && !have_L) {
+                    // first tile of a CTA that does not own the diagonal block: wait for it
+                    if (tid == 0) {
+                        while ((int)(ld_acquire(gsync + 1) - seq) < 0) {
+                        }
+                    }
+                    __syncthreads();
+                    if (ld_acquire(gsync + 2) == ordinal + 1) {
+                        fail = (int)ld_acquire(gsync + 3);
+                        // the tail of this tile has already put the first chunks of this CTA's next
+                        // tile into the ring: take them out again so the ring stays in step
+                        if (it + G < ntile && nk > 0) {
+                            for (int s0 = 0; s0 < NSTAGE; ++s0) {
+                                mbar_wait(bar_full + 8 * use_s, use_k & 1);
+                                __syncwarp();
+                                if (lane == 0) atomicAdd(released + use_s, 1);
+                                if (++use_s == NSTAGE) { use_s = 0; ++use_k; }
+                            }
+                        }
+                        break;
+                    }
+                    for (int idx = tid; idx < 36 * 64; idx += THREADS) {
+                        const int blk = idx >> 6, r8 = (idx >> 3) & 7, c8 = idx & 7;
+                        int bi = 0;
+                        while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
+                        const int bj = blk - bi * (bi + 1) / 2;
+                        const int r = 8 * bi + r8, c = 8 * bj + c8;
+                        Ld[idx] = (r < nv && c < nv) ? __ldcg(Kb + (size_t)(j0 + r) * ld + j0 + c)
+                                                     : (r == c ? 1.0 : 0.0);
+                    }
+                    Dinv[tid] = __ldcg(gdinv + tid);
+                    Dinv[tid + THREADS] = __ldcg(gdinv + tid + THREADS);
+                    __syncthreads();
+                    have_L = true;
                 }
                 // the stage area is idle from here to the next contraction loop: start the next
                 // tile's first chunks now so they land while the triangular solve runs
                 // (the tail of every other tile has already refilled the ring for its successor)
-                if (it == 0 && ntile > 1 && tid == 0) {
+                if (it == 0 && G < ntile && tid == 0) {
 #pragma unroll
                     for (int s0 = 0; s0 < NSTAGE; ++s0)
-                        if (s0 < nk) tma_chunk((use_s + s0) % NSTAGE, s0, i0 + TM);
+                        if (s0 < nk) tma_chunk((use_s + s0) % NSTAGE, s0, i0 + G * TM);
                 }
                 if ((DBG & 16) && tr_) tr_[5] = clock64();
                 // fragments that still need the solve: real rows, not part of the diagonal block
@@ -539,11 +641,28 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
         }
 
         // ---- -1/2 z.z - sum log L_ii - n/2 log(2 pi) ----
+        if (COOP) {
+            // every CTA adds the log-determinant of the diagonal blocks it owned; CTA 0 of the
+            // group then finishes alone (two accumulators, alternating, so the next matrix's
+            // additions cannot meet this matrix's read-and-reset)
+            double* const gld = reinterpret_cast<double*>(gsync + 4) + (ordinal & 1);
+            if (tid == 0 && logdet != 0.0) atomicAdd(gld, logdet);
+            group_barrier();
+            if (!fail && ld_acquire(gsync + 2) == ordinal + 1) fail = (int)ld_acquire(gsync + 3);
+            if (rank != 0) continue;
+            if (tid == 0) {
+                logdet = __ldcg(gld);
+                *gld = 0.0;
+            }
+        }
         __syncthreads();
         double q = 0.0;
         if (!fail) {
             const double* z = Kb + (size_t)n * ld;
-            for (int c = tid; c < n; c += THREADS) q += z[c] * z[c];
+            for (int c = tid; c < n; c += THREADS) {
+                const double zc = COOP ? __ldcg(z + c) : z[c];
+                q += zc * zc;
+            }
         }
         q = warp_sum(q);
         if (lane == 0) red[warp] = q;
@@ -609,18 +728,48 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
     const int slots = 2 * h->sm_count;      // two resident CTAs per SM (registers and shared memory)
     const int grid = batch < slots ? batch : slots;
     cudaStream_t st = (cudaStream_t)stream;
+    p.group = 1;
+    p.sync = nullptr;
+    p.dinv = nullptr;
+    p.trace = nullptr;
+    {
+        // Fewer matrices than CTA slots: several CTAs per matrix, at most one per row tile of the
+        // first block column.  MF_COOP_GROUP overrides the choice (1 = never; tests use it).
+        const int ntile0 = (n + 1 + pf::TM - 1) / pf::TM;
+        int G = slots / batch;
+        if (G > ntile0) G = ntile0;
+        const char* eg = getenv("MF_COOP_GROUP");
+        if (eg) G = atoi(eg);
+        if (G > slots) G = slots;
+        if (G > h->coop_groups) G = h->coop_groups;
+        if (G >= 2 && !getenv("MF_DBG")) {
+            int ngroups = slots / G;
+            if (ngroups > batch) ngroups = batch;
+            p.group = G;
+            p.sync = h->coop_sync;
+            p.dinv = h->coop_dinv;
+            MF_CUDA_CHECK(h, cudaMemsetAsync(h->coop_sync, 0, (size_t)h->coop_groups * 8 * sizeof(unsigned), st));
+            MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<3, 2, 0, 1>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  pf::smem_bytes(3)));
+            void* args[] = {(void*)&p};
+            MF_CUDA_CHECK(h, cudaLaunchCooperativeKernel((const void*)pf::mf_potrf_ll_kernel<3, 2, 0, 1>,
+                                                         dim3(ngroups * G), dim3(pf::THREADS), args,
+                                                         pf::smem_bytes(3), st));
+            return MF_OK;
+        }
+    }
 #define MF_LAUNCH(DBG_)                                                                            \
     do {                                                                                           \
-        MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<3, 2, DBG_>,                  \
+        MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<3, 2, DBG_, 0>,               \
                                               cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                               pf::smem_bytes(3)));                                 \
-        pf::mf_potrf_ll_kernel<3, 2, DBG_><<<grid, pf::THREADS, pf::smem_bytes(3), st>>>(p);       \
+        pf::mf_potrf_ll_kernel<3, 2, DBG_, 0><<<grid, pf::THREADS, pf::smem_bytes(3), st>>>(p);    \
     } while (0)
     // MF_DBG selects one of the timing-experiment instantiations (scripts/gpu_sweep.sh,
     // scripts/trace_run.py); results of those launches are not valid likelihoods
     const char* ed = getenv("MF_DBG");
     const int dbg = ed ? atoi(ed) : 0;
-    p.trace = nullptr;
     if (dbg == 16) {
         const size_t words = (size_t)grid * 200 * 8;
         MF_CUDA_CHECK(h, cudaMalloc(&p.trace, words * 8));

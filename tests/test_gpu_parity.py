@@ -180,6 +180,43 @@ def test_factor_and_z_against_lapack(mf):
         assert rel_err(float(ll2[b]), go.loglike_from_matrix(Kref, R[b])) <= LL_RTOL
 
 
+@pytest.mark.parametrize("N,G", [(30, 2), (70, 2), (70, 5), (200, 3), (500, 4), (500, 12)])
+def test_cooperative_groups_match_one_cta_per_matrix(mf, monkeypatch, N, G):
+    """Several CTAs per matrix (the path taken when the batch is smaller than the GPU) give the
+    same factor, bit for bit, as one CTA per matrix; failures stay per sample."""
+    from miniframe_b200._engine import Engine
+    eng = Engine.get()
+    t, (rv, rhk, bis), (e1, e2, e3) = go.synthetic_series(N, seed=5)
+    gp = mf.BIGgp.BIGgp(mf.kernels.SquaredExponential, [None, None, None], t, rv, e1, rhk, e2, bis, e3)
+    n = 3 * N
+    good1 = [3.0, 0.5, 1.0, 0.5, 0.8, 0.9, 0.4]
+    good2 = [20.0, 0.03, 1.0, 0.5, 0.8, 0.9, 0.4]
+    bad = [5000.0, 0.0, 1e8, 1e8, 1e8, 1e8, 1e8]
+    A = np.array([good1, bad, good2, good1, bad])
+    prob = gp._problem(N)
+    resid = eng.tensor(go.biggp_y(rv, rhk, bis)[None, :])
+    out = {}
+    for g in (1, G):
+        monkeypatch.setenv("MF_COOP_GROUP", str(g))
+        Kd = eng.build_cov(prob, eng.tensor(t), eng.tensor(gp._diag_yerr()), eng.tensor(A), None, full=False)
+        ll, info = eng.potrf_loglike(Kd, n, resid)
+        out[g] = (Kd.cpu().numpy(), ll.cpu().numpy(), info.cpu().numpy())
+    K1, ll1, info1 = out[1]
+    KG, llG, infoG = out[G]
+    assert np.array_equal(info1, infoG)
+    assert (info1 != 0).tolist() == [False, True, False, False, True]
+    y = go.biggp_y(rv, rhk, bis)
+    for b in (0, 2, 3):
+        L1 = np.tril(K1[b, :n, :n])
+        LG = np.tril(KG[b, :n, :n])
+        assert np.array_equal(L1, LG)
+        assert np.array_equal(K1[b, n, :n], KG[b, n, :n])
+        assert rel_err(float(llG[b]), float(ll1[b])) <= 1e-13
+        want = go.biggp_loglike_literal("SquaredExponential", A[b], t, y, e1, e2, e3)
+        assert rel_err(float(llG[b]), want) <= LL_RTOL
+    assert np.all(np.isinf(llG[[1, 4]])) and np.all(llG[[1, 4]] < 0)
+
+
 def test_batch_mixes_failures_and_successes(mf, golden):
     """Non-positive-definite samples give -inf for themselves only."""
     d = golden.data("spot40")
