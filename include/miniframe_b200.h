@@ -135,6 +135,10 @@ int mf_build_cov(mf_handle_t h, const mf_problem_t* prob, int batch,
  *          the whole batch), or NULL (z = 0, ll = -logdet - n/2 log 2pi)
  *   ll     [batch] log-likelihood, -inf where info != 0
  *   info   [batch]
+ * One CTA per matrix when batch >= 2 x SM count; with fewer matrices several CTAs
+ * share each one (cooperative launch; the handle's scratch carries their
+ * synchronisation words, so use one handle per stream).  The factor is the same,
+ * bit for bit, either way.
  */
 int mf_potrf_loglike(mf_handle_t h, int batch, int n,
                      double* K, int64_t ld, int64_t stride,
