@@ -753,10 +753,17 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
                                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   pf::smem_bytes(3)));
             void* args[] = {(void*)&p};
-            MF_CUDA_CHECK(h, cudaLaunchCooperativeKernel((const void*)pf::mf_potrf_ll_kernel<3, 2, 0, 1>,
-                                                         dim3(ngroups * G), dim3(pf::THREADS), args,
-                                                         pf::smem_bytes(3), st));
-            return MF_OK;
+            const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)pf::mf_potrf_ll_kernel<3, 2, 0, 1>,
+                                                               dim3(ngroups * G), dim3(pf::THREADS), args,
+                                                               pf::smem_bytes(3), st);
+            if (ce == cudaSuccess) return MF_OK;
+            if (ce != cudaErrorCooperativeLaunchTooLarge) {
+                snprintf(h->err, sizeof(h->err), "cooperative launch failed: %s", cudaGetErrorString(ce));
+                return MF_ERR_CUDA;
+            }
+            // the CTAs cannot all be resident (SMs shared with another context): one CTA per matrix
+            (void)cudaGetLastError();
+            p.group = 1;
         }
     }
 #define MF_LAUNCH(DBG_)                                                                            \
