@@ -133,7 +133,14 @@ class GPBase(object):
             ex = eng.tensor(extra)
             if ex.ndim != 2 or ex.shape != (B, prob.extra_len):
                 raise ValueError("expected extra parameters of shape (%d, %d)" % (B, prob.extra_len))
-        resid = eng.tensor(self._residual_rows(Bm, B))
+        if self.mean_pars_size == 0:
+            # no mean function takes parameters: the residual is the same constant row for every
+            # call, keep it on the device (a sampler calls this thousands of times)
+            if Bm is not None and np.size(Bm.detach().cpu() if _is_torch(Bm) else Bm) != 0:
+                raise AssertionError("mean parameters given but no mean function takes any")
+            resid = self._dev("resid_no_mean_pars", lambda: self._residual_rows(None, B))
+        else:
+            resid = eng.tensor(self._residual_rows(Bm, B))
         t = self._dev("t", lambda: np.asarray(self.t, dtype=float))
         diag = self._dev(diag_key, diag_make)
         ll, info = eng.loglike(prob, t, diag, hyper, ex, resid)

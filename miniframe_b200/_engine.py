@@ -64,6 +64,9 @@ class Engine(object):
         """A cached byte buffer holding as many of `batch` matrices as memory allows."""
         torch = _torch()
         per = self.matrix_stride(n) * 8
+        if (self._ws is not None and self._ws.numel() >= batch * per and
+                (self.max_workspace_bytes is None or batch * per <= self.max_workspace_bytes)):
+            return self._ws, batch * per          # the cached buffer already holds the whole batch
         cap = self.max_workspace_bytes
         if cap is None:
             free, _ = torch.cuda.mem_get_info(self.device)
