@@ -773,7 +773,7 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
                                               pf::smem_bytes(3)));                                 \
         pf::mf_potrf_ll_kernel<3, 2, DBG_, 0><<<grid, pf::THREADS, pf::smem_bytes(3), st>>>(p);    \
     } while (0)
-    // MF_DBG selects one of the timing-experiment instantiations (scripts/gpu_sweep.sh,
+    // MF_DBG selects one of the timing-experiment instantiations (scripts/gpu_env_sweep.sh,
     // scripts/trace_run.py); results of those launches are not valid likelihoods
     const char* ed = getenv("MF_DBG");
     const int dbg = ed ? atoi(ed) : 0;
