@@ -742,20 +742,27 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
         if (eg) G = atoi(eg);
         if (G > slots) G = slots;
         if (G > h->coop_groups) G = h->coop_groups;
+        // One CTA per SM instead of two when that still gives every tile of the first block column
+        // its own CTA, or when there is a single matrix: a CTA that has its SM to itself runs a
+        // tile ~1.75x faster than two sharing one, and which CTAs share an SM cannot be chosen.
+        const int per_sm1 = h->sm_count / batch;          // group size with one CTA per SM
+        const bool alone = !eg && per_sm1 >= 2 && (batch == 1 || per_sm1 >= ntile0);
+        if (alone) G = per_sm1 < ntile0 ? per_sm1 : ntile0;
         if (G >= 2 && !getenv("MF_DBG")) {
-            int ngroups = slots / G;
+            int ngroups = (alone ? h->sm_count : slots) / G;
             if (ngroups > batch) ngroups = batch;
+            // a dynamic shared-memory request above half an SM keeps a second CTA off the SM
+            const int smem = alone ? 120 * 1024 : pf::smem_bytes(3);
             p.group = G;
             p.sync = h->coop_sync;
             p.dinv = h->coop_dinv;
             MF_CUDA_CHECK(h, cudaMemsetAsync(h->coop_sync, 0, (size_t)h->coop_groups * 8 * sizeof(unsigned), st));
             MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<3, 2, 0, 1>,
-                                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  pf::smem_bytes(3)));
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
             void* args[] = {(void*)&p};
             const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)pf::mf_potrf_ll_kernel<3, 2, 0, 1>,
                                                                dim3(ngroups * G), dim3(pf::THREADS), args,
-                                                               pf::smem_bytes(3), st);
+                                                               smem, st);
             if (ce == cudaSuccess) return MF_OK;
             if (ce != cudaErrorCooperativeLaunchTooLarge) {
                 snprintf(h->err, sizeof(h->err), "cooperative launch failed: %s", cudaGetErrorString(ce));
