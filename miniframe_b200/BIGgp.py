@@ -179,6 +179,72 @@ class BIGgp(GPBase):
     def minus_log_likelihood(self, a, b, nugget=True):
         return -self.log_likelihood(a, b, nugget=True)
 
+    # ---- prediction -----------------------------------------------
+    _MODELS = {"rv": (0, 0, 0), "rhk": (1, 2, 2), "bis": (2, 1, 1)}   # block, chunk of y, mean slot
+
+    def _predict(self, time, a, b, model, extra_diag=0.0):
+        """Conditional predictive distribution of ONE series given its own data
+        (reference BIGgp.py:570-641), on the device:
+          * one covariance build on the concatenated times [time, t] gives K** (k11(a, time)),
+            K* (no white noise: the reference's non-square branch, kernels.py:299-304) and
+            K (k11(a, t)) as sub-blocks of the series' diagonal block;
+          * the factorisation kernel factors K with the residual as row n (z = L^-1 r);
+          * V = L^-1 K*^T is a forward substitution with T right-hand sides on that one factor;
+          * mean = V^T z + m(time), cov = K** - V^T V (a plain library GEMM, not a hot path).
+        Quirks kept: y is ordered [rv, bis, rhk] but the blocks [rv, rhk, bis] (Q2), so 'rhk'
+        reads chunk 2 and mean slot 2, 'bis' chunk 1 and slot 1; the covariance being
+        conditioned on carries NO observational errors (only wn^2, and the jitter in PlusJitt);
+        when len(time) == len(t) every kernel class adds wn^2 on the diagonal of K* too."""
+        import torch
+        if model not in self._MODELS:
+            raise UnboundLocalError("model must be 'rv', 'rhk' or 'bis'")   # the reference falls through
+        blk, chunk, slot = self._MODELS[model]
+        eng = self.engine
+        time = np.asarray(time, dtype=float)
+        T, N = time.size, self.t.size
+        self.mean_pars = b
+        if self.means[slot] is None:
+            raise TypeError("'NoneType' object is not callable")           # BIGgp.py:609 with no mean
+        r = np.array_split(self.y - self.mean(), 3)[chunk]
+        mean_val = np.asarray(self.means[slot](time), dtype=float)
+        hyper = self._hyper_row(a)
+        self._check_finite(hyper)
+        x = np.concatenate([time, np.asarray(self.t, dtype=float)])
+        m = x.size
+        prob = self._problem(m)
+        Kbig = eng.build_cov(prob, eng.tensor(x), eng.tensor(np.zeros(3 * m)), eng.tensor(hyper), None, full=True)
+        S = Kbig[0, blk * m:(blk + 1) * m, blk * m:(blk + 1) * m]
+        Kss = S[:T, :T].clone()
+        Ks = S[:T, T:].contiguous()                       # (T, N)
+        if extra_diag:
+            Kss += extra_diag * torch.eye(T, dtype=torch.float64, device=Kss.device)
+        if T == N:
+            # square tstar: the four kernel-class calls each add wn^2 I (kernels.py:296)
+            npar = _lib.KERNEL_NPAR[self._kernel_id()]
+            wn = float(hyper[0, npar - 1])
+            vc, vr, lc, bc, br = (float(v) for v in hyper[0, npar:npar + 5])
+            cw = {0: (vc + vr) ** 2, 1: lc * lc, 2: (bc + br) ** 2}[blk]
+            Ks += cw * wn * wn * torch.eye(T, dtype=torch.float64, device=Ks.device)
+        ld, stride = eng.ld(N), eng.matrix_stride(N)
+        Kw = torch.zeros((1, stride // ld, ld), dtype=torch.float64, device=Ks.device)
+        Kw[0, :N, :N] = S[T:, T:]
+        if extra_diag:
+            Kw[0, :N, :N] += extra_diag * torch.eye(N, dtype=torch.float64, device=Ks.device)
+        ll, info = eng.potrf_loglike(Kw, N, eng.tensor(r[None, :]))
+        if int(info[0]) != 0:
+            raise np.linalg.LinAlgError("%d-th leading minor of the array is not positive definite"
+                                        % int(info[0]))                    # scipy cho_factor, uncaught
+        z = Kw[0, N, :N]
+        V, _ = eng.solve_logdet(Kw, N, Ks, None, shared=True)               # (T, N): rows L^-1 K*_i
+        y_mean = V @ z + eng.tensor(mean_val)
+        y_cov = Kss - V @ V.T
+        y_std = torch.sqrt(torch.diagonal(y_cov))
+        return y_mean.cpu().numpy(), y_std.cpu().numpy(), y_cov.cpu().numpy()
+
+    def predict_gp(self, time, a, b, model='rv'):
+        """y_mean, y_std, y_cov of the chosen series at ``time`` (reference BIGgp.py:570-641)."""
+        return self._predict(time, a, b, model)
+
     def log_likelihood_batch(self, A, Bm=None):
         """log_likelihood for every row of ``A`` (B, 9 | 7) in one device pass.
         ``Bm`` (B, mean_pars_size) holds the mean parameters per row when the

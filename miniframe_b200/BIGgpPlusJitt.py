@@ -40,6 +40,14 @@ class BIGgp(_plain.BIGgp):
             raise TypeError("log_likelihood() missing 1 required positional argument: 'c'")
         return -self.log_likelihood(a, b, c, nugget=True)
 
+    def predict_gp(self, time, a, b, c, model='rv'):
+        """As BIGgp.predict_gp with the series' jitter^2 added to the covariance being conditioned
+        on and to K** (BIGgpPlusJitt.py:576-653).  The jitters are read in the order of y,
+        [rv, bis, rhk]: 'rhk' takes c[2] and 'bis' c[1]."""
+        c = np.asarray(c, dtype=float).ravel()
+        idx = {"rv": 0, "rhk": 2, "bis": 1}.get(model, 0)
+        return self._predict(time, a, b, model, extra_diag=float(c[idx]) ** 2)
+
     def log_likelihood_batch(self, A, Bm=None, C=None):
         """Rows of ``A`` (B, 9 | 7) with jitters ``C`` (B, 3)."""
         if C is None:

@@ -107,10 +107,12 @@ class Engine(object):
         self.launches += 1
         return ll, info
 
-    def solve_logdet(self, L, n, resid, info=None):
+    def solve_logdet(self, L, n, resid, info=None, shared=False):
+        """z = L^-1 resid (and the log-likelihood terms) per matrix; ``shared``: ONE factor,
+        L[0], for every row of ``resid`` (a multi-right-hand-side forward substitution)."""
         torch = _torch()
-        B = L.shape[0]
-        ld, stride = L.shape[2], L.shape[1] * L.shape[2]
+        B = resid.shape[0] if shared else L.shape[0]
+        ld, stride = L.shape[2], (0 if shared else L.shape[1] * L.shape[2])
         ll = torch.empty(B, dtype=torch.float64, device=self.device)
         z = torch.empty((B, n), dtype=torch.float64, device=self.device)
         rs = 0 if resid.shape[0] == 1 else resid.shape[1]

@@ -353,3 +353,31 @@ def test_abi_argument_errors(mf):
     st = eng.lib.mf_potrf_loglike(eng.handle, 1, 12, eng.ptr(buf), 12, 13 * 12, None, 0, eng.ptr(buf),
                                   eng.ptr(buf), eng.stream())
     assert st == 1
+
+
+def test_predict_gp_against_reference_golden(mf):
+    """predict_gp against outputs of the unmodified reference
+    (tests/golden/make_golden_predict.py): non-square, square (wn quirk) and on-data grids."""
+    import json
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    d = np.load(os.path.join(here, "golden_predict_v1.npz"))
+    meta = json.load(open(os.path.join(here, "golden_predict_v1.json")))
+    means = [mf.means.Constant, mf.means.Linear, mf.means.Constant]
+    for case in meta["cases"]:
+        jit = case.get("jitter")
+        cls = mf.BIGgpPlusJitt.BIGgp if jit else mf.BIGgp.BIGgp
+        gp = cls(getattr(mf.kernels, case["kernel"]), list(means), d["t"], d["rv"], d["rverr"],
+                 d["rhk"], d["sig_rhk"], d["bis"], d["sig_bis"])
+        args = (d[case["grid"]], case["a"], case["b"]) + ((jit,) if jit else ())
+        mean, std, cov = gp.predict_gp(*args, model=case["model"])
+        name = case["name"]
+        wm, ws, wc = d[name + "_mean"], d[name + "_std"], d[name + "_cov"]
+        # measured: mean 2e-13, covariance 7e-13 of max|cov|, std 1e-9 relative (K** - K* K^-1 K*^T
+        # cancels; K carries only wn^2 on its diagonal, no observational errors)
+        scale = max(np.abs(wc).max(), 1e-300)
+        assert mean.shape == wm.shape and cov.shape == wc.shape
+        assert np.abs(mean - wm).max() <= 1e-10 * max(1.0, np.abs(wm).max()), name
+        assert np.abs(cov - wc).max() <= 1e-10 * scale, name
+        ok = np.isfinite(ws) & (ws > 1e-4 * np.sqrt(scale))
+        assert np.allclose(std[ok], ws[ok], rtol=1e-7, atol=0), name
