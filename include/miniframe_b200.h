@@ -162,7 +162,9 @@ int mf_loglike(mf_handle_t h, const mf_problem_t* prob, int batch,
  * Stand-alone fused forward substitution + log-determinant on an existing
  * factor (the cho_solve / log-diag tail, BIGgp.py:307-309), for callers that
  * reuse one factor with several residuals (e.g. sampling mean parameters only).
- *   L      lower factor in the workspace layout (row n is not read)
+ *   L      lower factor in the workspace layout (row n is not read); `stride` may be 0:
+ *          ONE factor for all `batch` right-hand sides (used by predict_gp for L^-1 K*^T,
+ *          BIGgp.py:635-637)
  *   z      [batch x n] out (row stride n), required (it is the kernel's working vector)
  *   info   factorisation status per sample or NULL; ll = -inf where info != 0
  */
