@@ -65,7 +65,7 @@ struct Params {
     // cooperative variant (COOP): `group` CTAs share one matrix; 8 words + 512 doubles per group
     int group;
     unsigned* sync;       // [0] barrier arrivals, [1] diagonal-block sequence number, [2] failed matrix
-                          // ordinal + 1, [3] info of the failure, [4..7] two log-det accumulators
+                          // ordinal + 1, [3] info of the failure
     double* dinv;
     long long* trace;     // DBG & 16: per-tile phase timestamps of the first matrix of each CTA
 };
@@ -200,7 +200,6 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
     for (int mat = grp; mat < p.batch; mat += ngroups, ++ordinal) {
         double* const Kb = p.K + (size_t)mat * p.stride;
         const double* const rb = p.resid ? p.resid + (size_t)mat * p.resid_stride : nullptr;
-        double logdet = 0.0;          // meaningful in warp 0 only
         int fail = 0;
         const int ncb = (n + NB - 1) / NB;
         {
@@ -509,12 +508,6 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
 #pragma unroll
                         for (int i = 0; i < 8; ++i) Dinv[bb * 64 + i * 8 + cc] = x[i];
                     }
-                    if (warp == 0) {              // sum of log L_ii of this block
-                        double lg = 0.0;
-                        if (lane < nv) lg += log(Ld[ldblk(lane >> 3, lane >> 3) + (lane & 7) * 9]);
-                        if (lane + 32 < nv) lg += log(Ld[ldblk((lane + 32) >> 3, (lane + 32) >> 3) + (lane & 7) * 9]);
-                        logdet += warp_sum(lg);
-                    }
                     // L_jj (and, when the block column is the last one, the z entries that
                     // live inside it) go back to global memory, one 512-byte row per warp pass
 #pragma unroll
@@ -641,35 +634,37 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
         }
 
         // ---- -1/2 z.z - sum log L_ii - n/2 log(2 pi) ----
+        // z (row n) and the diagonal of L are read back in one fixed order, whoever wrote them:
+        // the result is bit-identical for one CTA per matrix and for any cooperative group size.
         if (COOP) {
-            // every CTA adds the log-determinant of the diagonal blocks it owned; CTA 0 of the
-            // group then finishes alone (two accumulators, alternating, so the next matrix's
-            // additions cannot meet this matrix's read-and-reset)
-            double* const gld = reinterpret_cast<double*>(gsync + 4) + (ordinal & 1);
-            if (tid == 0 && logdet != 0.0) atomicAdd(gld, logdet);
-            group_barrier();
+            group_barrier();          // the other CTAs' rows are complete and visible
             if (!fail && ld_acquire(gsync + 2) == ordinal + 1) fail = (int)ld_acquire(gsync + 3);
-            if (rank != 0) continue;
-            if (tid == 0) {
-                logdet = __ldcg(gld);
-                *gld = 0.0;
-            }
+            if (rank != 0) continue;  // CTA 0 of the group finishes alone
         }
         __syncthreads();
-        double q = 0.0;
+        double q = 0.0, lg = 0.0;
         if (!fail) {
             const double* z = Kb + (size_t)n * ld;
             for (int c = tid; c < n; c += THREADS) {
                 const double zc = COOP ? __ldcg(z + c) : z[c];
+                const double dc = COOP ? __ldcg(Kb + (size_t)c * ld + c) : Kb[(size_t)c * ld + c];
                 q += zc * zc;
+                lg += log(dc);
             }
         }
         q = warp_sum(q);
-        if (lane == 0) red[warp] = q;
+        lg = warp_sum(lg);
+        if (lane == 0) {
+            red[warp] = q;
+            red[8 + warp] = lg;
+        }
         __syncthreads();
         if (tid == 0) {
-            double s = 0.0;
-            for (int w = 0; w < THREADS / 32; ++w) s += red[w];
+            double s = 0.0, logdet = 0.0;
+            for (int w = 0; w < THREADS / 32; ++w) {
+                s += red[w];
+                logdet += red[8 + w];
+            }
             p.ll[mat] = fail ? -INFINITY : (-0.5 * s - logdet - 0.5 * (double)n * log(2.0 * 3.141592653589793));
             p.info[mat] = fail;
         }

@@ -211,7 +211,7 @@ def test_cooperative_groups_match_one_cta_per_matrix(mf, monkeypatch, N, G):
         LG = np.tril(KG[b, :n, :n])
         assert np.array_equal(L1, LG)
         assert np.array_equal(K1[b, n, :n], KG[b, n, :n])
-        assert rel_err(float(llG[b]), float(ll1[b])) <= 1e-13
+        assert float(llG[b]) == float(ll1[b])          # same read-back order whoever wrote the rows
         want = go.biggp_loglike_literal("SquaredExponential", A[b], t, y, e1, e2, e3)
         assert rel_err(float(llG[b]), want) <= LL_RTOL
     assert np.all(np.isinf(llG[[1, 4]])) and np.all(llG[[1, 4]] < 0)
