@@ -111,6 +111,31 @@ class GPBase(object):
         self.mean_pars = keep
         return rows
 
+    def _residual_rows_device(self, Bm, batch):
+        """(batch, n) residuals on the device, every mean evaluated for the whole batch at once
+        (miniframe_b200.means.batch_eval); None when some mean class has no batched form."""
+        import torch
+        from . import means as _means
+        eng = self.engine
+        Bm = eng.tensor(Bm)
+        if Bm.ndim == 1:
+            Bm = Bm[None, :].expand(batch, -1)
+        assert tuple(Bm.shape) == (batch, self.mean_pars_size)
+        t = self._dev("t", lambda: np.asarray(self.t, dtype=float))
+        N = self.t.size
+        y = self._dev("y_flat", lambda: np.asarray(self._y_flat(), dtype=float))
+        rows = y[None, :].repeat(batch, 1)
+        k = 0
+        for i, m in enumerate(self.means):
+            if m is None:
+                continue
+            vals = _means.batch_eval(m, t, Bm[:, k:k + m._parsize])
+            if vals is None:
+                return None
+            rows[:, i * N:(i + 1) * N] -= vals
+            k += m._parsize
+        return rows
+
     @staticmethod
     def _check_finite(*arrays):
         # scipy's cho_factor(check_finite=True) raises ValueError on NaN/Inf and the
@@ -140,7 +165,12 @@ class GPBase(object):
                 raise AssertionError("mean parameters given but no mean function takes any")
             resid = self._dev("resid_no_mean_pars", lambda: self._residual_rows(None, B))
         else:
-            resid = eng.tensor(self._residual_rows(Bm, B))
+            if Bm is None:
+                raise ValueError("this model has %d mean parameters: pass one row per sample"
+                                 % self.mean_pars_size)
+            resid = self._residual_rows_device(Bm, B)
+            if resid is None:                       # a mean class without a batched form
+                resid = eng.tensor(self._residual_rows(Bm, B))
         t = self._dev("t", lambda: np.asarray(self.t, dtype=float))
         diag = self._dev(diag_key, diag_make)
         ll, info = eng.loglike(prob, t, diag, hyper, ex, resid)

@@ -193,3 +193,58 @@ class TOI175keplerians(MeanModel):
             T0 = t[0] - (P * phi) / (2. * np.pi)
             rv = rv + _kepler_rv(t, P, K, e, w, T0, iterations=iters)
         return rv + total
+
+
+# ---- batched evaluation (one row of parameters per sample) --------------------------------
+# The GP classes evaluate a whole ensemble of mean-parameter sets at once.  For the classes of
+# this module that is a handful of element-wise torch operations on a (B, N) tensor - on the
+# device when the parameters live there - written in the same operation order as the scalar
+# numpy ``__call__`` above, so both agree to the last couple of ulp of sin/cos.  Returns None for
+# any other class (user-defined means, Sum): the caller then loops over ``__call__`` on the host.
+def _kepler_rv_batch(torch, t, P, K, e, w, T0, iterations):
+    M = 2 * np.pi * (t - T0) / P
+    E0 = M + e * torch.sin(M) + 0.5 * (e ** 2) * torch.sin(2 * M)
+    M0 = E0 - e * torch.sin(E0)
+    for _ in range(iterations):
+        aux = M - M0
+        E1 = E0 + aux / (1 - e * torch.cos(E0))
+        M1 = E0 - e * torch.sin(E0)
+        E0, M0 = E1, M1
+    nu = 2 * torch.atan(torch.sqrt((1 + e) / (1 - e)) * torch.tan(E0 / 2))
+    return K * (e * torch.cos(w) + torch.cos(w + nu))
+
+
+def batch_eval(mean, t, pars):
+    """``mean``: an instance of a class of this module; ``t``: (N,) float64 tensor;
+    ``pars``: (B, mean._parsize) tensor on the same device.  Returns the (B, N) tensor of
+    m(t; pars[b]) or None when the class has no batched form."""
+    import torch
+    cls = type(mean)
+    c = [pars[:, k:k + 1] for k in range(pars.shape[1])]
+    tt = t[None, :]
+    if cls is Constant:
+        return c[0].expand(-1, t.numel()).clone()
+    if cls is Linear:
+        tmean = float(np.asarray(t.detach().cpu()).mean())      # numpy's mean, as the scalar path
+        return c[0] * (tt - tmean) + c[1]
+    if cls in (Parabola, Cubic):
+        y = torch.zeros((pars.shape[0], t.numel()), dtype=t.dtype, device=t.device)
+        for k in range(pars.shape[1]):                           # np.polyval's Horner order
+            y = y * tt + c[k]
+        return y
+    if cls is Sine:
+        return c[0] * torch.sin((2 * np.pi * tt / c[1]) + c[2]) + c[3]
+    if cls is oldKeplerian:
+        return _kepler_rv_batch(torch, tt, c[0], c[1], c[2], c[3], c[4], 100)
+    if cls is Keplerian:
+        T0 = t[0] - (c[0] * c[4]) / (2. * np.pi)
+        return _kepler_rv_batch(torch, tt, c[0], c[1], c[2], c[3], T0, 100) + c[5]
+    if cls is TOI175keplerians:
+        total = c[15].expand(-1, t.numel())
+        rv = 0.0
+        for k, iters in ((0, 500), (1, 100), (2, 100)):
+            P, K, e, w, phi = c[5 * k:5 * k + 5]
+            T0 = t[0] - (P * phi) / (2. * np.pi)
+            rv = rv + _kepler_rv_batch(torch, tt, P, K, e, w, T0, iters)
+        return rv + total
+    return None

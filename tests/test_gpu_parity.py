@@ -355,6 +355,30 @@ def test_abi_argument_errors(mf):
     assert st == 1
 
 
+def test_batched_keplerian_and_sine_means(mf, golden):
+    """Per-sample mean parameters evaluated on the device for the whole batch (Keplerian: the
+    reference's 100 fixed-point steps), against the oracle fed with the reference-style residual."""
+    d = golden.data("synth64")
+    gp = mf.BIGgp.BIGgp(mf.kernels.QuasiPeriodic, [mf.means.Keplerian, mf.means.Sine, mf.means.Cubic],
+                        t=d["t"], rv=d["rv"], rverr=d["rverr"], rhk=d["rhk"], sig_rhk=d["sig_rhk"],
+                        bis=d["bis"], sig_bis=d["sig_bis"])
+    rng = np.random.default_rng(12)
+    B = 9
+    H = go.synthetic_biggp_hypers(B, seed=6)
+    Bm = np.column_stack([rng.uniform(5, 30, B), rng.uniform(0.1, 2, B), rng.uniform(0, 0.5, B),
+                          rng.uniform(0, 6, B), rng.uniform(0, 6, B), rng.normal(0, 0.1, B),
+                          rng.uniform(0.1, 1, B), rng.uniform(5, 30, B), rng.uniform(0, 6, B), rng.normal(0, 0.1, B),
+                          rng.normal(0, 1e-6, B), rng.normal(0, 1e-4, B), rng.normal(0, 1e-2, B), rng.normal(0, 0.1, B)])
+    assert gp.mean_pars_size == Bm.shape[1] == 14
+    got = gp.log_likelihood_batch(H, Bm)
+    for i in range(B):
+        gp.mean_pars = Bm[i]
+        resid = gp.y - gp.mean()                      # host numpy, as the reference does (BIGgp.py:303)
+        K = go.biggp_matrix_literal("QuasiPeriodic", H[i], d["t"], d["rverr"], d["sig_rhk"], d["sig_bis"])
+        assert rel_err(got[i], go.loglike_from_matrix(K, resid)) <= LL_RTOL
+    assert rel_err(gp.log_likelihood(H[3], Bm[3]), float(got[3])) <= 1e-12
+
+
 def test_predict_gp_against_reference_golden(mf):
     """predict_gp against outputs of the unmodified reference
     (tests/golden/make_golden_predict.py): non-square, square (wn quirk) and on-data grids."""

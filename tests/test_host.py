@@ -166,3 +166,31 @@ def test_smallgp_constructor_and_packing():
     assert np.array_equal(hyper[0], a) and np.array_equal(extra[0], [3.0, 0.1, 0.5, 0.6, 0.7])
     with pytest.raises(AssertionError):
         SMALLgp(kernels.QuasiPeriodic, None, [None, None], t, y1, e1, y2, e2, y3, e3)
+
+
+def test_batched_means_match_the_scalar_classes():
+    """means.batch_eval (torch, one parameter row per sample) against each class's numpy __call__."""
+    import torch
+    from miniframe_b200 import means
+    rng = np.random.default_rng(4)
+    t = np.sort(rng.uniform(0.0, 80.0, 57))
+    tt = torch.as_tensor(t)
+    cases = {means.Constant: lambda: [rng.normal()],
+             means.Linear: lambda: list(rng.normal(size=2)),
+             means.Parabola: lambda: list(rng.normal(size=3) * [1e-3, 1e-1, 1]),
+             means.Cubic: lambda: list(rng.normal(size=4) * [1e-5, 1e-3, 1e-1, 1]),
+             means.Sine: lambda: [rng.uniform(0.5, 3), rng.uniform(5, 40), rng.uniform(0, 6), rng.normal()],
+             means.oldKeplerian: lambda: [rng.uniform(5, 40), rng.uniform(1, 10), rng.uniform(0, 0.6), rng.uniform(0, 6), rng.uniform(0, 30)],
+             means.Keplerian: lambda: [rng.uniform(5, 40), rng.uniform(1, 10), rng.uniform(0, 0.6), rng.uniform(0, 6), rng.uniform(0, 6), rng.normal()],
+             means.TOI175keplerians: lambda: [v for _ in range(3) for v in (rng.uniform(2, 40), rng.uniform(1, 5), rng.uniform(0, 0.4), rng.uniform(0, 6), rng.uniform(0, 6))] + [rng.normal()]}
+    for cls, draw in cases.items():
+        P = np.array([draw() for _ in range(5)])
+        got = means.batch_eval(cls.initialize(), tt, torch.as_tensor(P)).numpy()
+        want = np.array([cls(*row)(t) for row in P])
+        assert got.shape == want.shape == (5, t.size)
+        assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max()), cls.__name__
+    class Custom(means.MeanModel):
+        _parsize = 1
+        def __call__(self, t):
+            return self.pars[0] * np.ones_like(t)
+    assert means.batch_eval(Custom.initialize(), tt, torch.zeros((2, 1), dtype=torch.float64)) is None
