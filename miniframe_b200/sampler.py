@@ -28,15 +28,17 @@ def _torch():
     return torch
 
 
-def box_log_prob(gp, log_lo, log_hi, extra=None):
+def box_log_prob(gp, log_lo, log_hi, transform=None):
     """The reference example's ``logprob`` (examples/BIGgp_mcmc.py:48-65) for a batch.
 
     Walkers live in log-parameter space; outside the box ``[log_lo, log_hi]`` the
     log-probability is -inf, inside it is ``gp.log_likelihood(exp(p), [])`` (the
     example's log-prior is the constant 0.0).  Rows outside the box are not sent
-    to the GPU at all.  ``extra``: optional callable ``P_inside -> tuple`` of further
-    arguments for ``gp.log_likelihood_batch`` (e.g. the jitter columns of
-    BIGgpPlusJitt).
+    to the GPU at all.  ``transform``: optional callable mapping the rows inside the
+    box to the argument tuple of ``gp.log_likelihood_batch`` - default
+    ``lambda P: (exp(P),)``; e.g. ``lambda P: (exp(P[:, :9]), P[:, 9:])`` samples nine
+    log kernel parameters and linear mean parameters (Keplerian orbit ...), and
+    ``lambda P: (exp(P[:, :9]), None, exp(P[:, 9:]))`` adds BIGgpPlusJitt's jitters.
     """
     torch = _torch()
 
@@ -48,8 +50,8 @@ def box_log_prob(gp, log_lo, log_hi, extra=None):
         idx = torch.nonzero(inside).flatten()
         if idx.numel():
             Pin = P.index_select(0, idx)
-            args = () if extra is None else tuple(extra(Pin))
-            ll = gp.log_likelihood_batch(torch.exp(Pin), *args)
+            args = (torch.exp(Pin),) if transform is None else tuple(transform(Pin))
+            ll = gp.log_likelihood_batch(*args)
             out.index_copy_(0, idx, ll.to(P.dtype))
         return out
 
