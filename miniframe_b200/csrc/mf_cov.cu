@@ -14,8 +14,6 @@
 //   * the per-sample coefficient table (kernel constants, block coefficients) is
 //     computed once per CTA and sample, in parallel over threads, and staged in shared
 //     memory together with the time arrays; a CTA walks many tiles of one sample.
-#include <stdlib.h>
-
 #include "mf_cov.cuh"
 
 namespace {
@@ -349,9 +347,7 @@ extern "C" int mf_build_cov(mf_handle_t h, const mf_problem_t* prob, int batch, 
     const bool high = prob->framework == MF_FRAMEWORK_SMALLGP;
     if (!high && !p.full && prob->nugget == 0.0) {
         const int by = batch < 65535 ? batch : 65535;
-        int bx = cov_ctas_per_sample(h, by, p.n_tiles);
-        if (getenv("MF_COV_BX")) bx = atoi(getenv("MF_COV_BX"));
-        if (bx > p.n_tiles) bx = p.n_tiles;
+        const int bx = cov_ctas_per_sample(h, by, p.n_tiles);
         dim3 grid(bx, by);
         const size_t smem = ((sizeof(SampleCoefs) + 15) / 16) * 16 +
                             (size_t)(2 * 3 * TT * TLD + N) * sizeof(double);
