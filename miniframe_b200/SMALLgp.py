@@ -167,6 +167,72 @@ class SMALLgp(GPBase):
     def minus_log_likelihood(self, a, b=[], c=[], nugget=True):
         return -self.log_likelihood(a, b, c, nugget=True)
 
+    # ---- prediction -----------------------------------------------
+    def predict_gp(self, time, a, b=[], c=[], model=1):
+        """Conditional predictive distribution of series ``model`` (1-based) given its own data
+        (reference SMALLgp.py:317-368), on the device like BIGgp.predict_gp.  The reference's
+        K* is NOT the kii formula evaluated at time - t: its a1 a3 term has the opposite sign
+        (+2 a1 a3 ddK instead of kii's -2 a1 a3 ddK, SMALLgp.py:353-358 vs 165-170) and the
+        extra kernel is left out (commented, 343-349).  Three covariance builds on the
+        concatenated times [time, t] give the pieces: the full kii (K**, K), kii without the
+        extra kernel (K* base) and ddK alone (the 4 a1 a3 correction).  No mean is added to
+        y_mean (the reference does not), there are no observational errors in K, and a square
+        K* (len(time) == len(t)) gets wn^2 (a1 + a2 + a3)^2 on its diagonal."""
+        import torch
+        M, N = self.number_models, self.t.size
+        if M < 2:
+            raise NotImplementedError("predict_gp needs at least two series on this path "
+                                      "(the single-series covariance build keeps quirk Q5)")
+        if not 1 <= int(model) <= M:
+            raise IndexError("model must be between 1 and %d" % M)
+        p = int(model) - 1
+        eng = self.engine
+        time = np.asarray(time, dtype=float)
+        T = time.size
+        self.mean_pars = b
+        r = np.array_split(np.concatenate(self.y, axis=0) - self.mean(), M)[p]
+        x = np.concatenate([time, np.asarray(self.t, dtype=float)])
+        m = x.size
+        A = np.asarray(a, dtype=float).ravel()[None, :]
+        prob = self._problem(m, nugget=False)
+        C = np.asarray(c, dtype=float).ravel()[None, :] if prob.extra_len else None
+        hyper, extra = self._pack(prob, A, C)
+        self._check_finite(hyper, extra)
+        xd, zd = eng.tensor(x), eng.tensor(np.zeros(M * m))
+
+        def block(pr, hy, ex):
+            K = eng.build_cov(pr, xd, zd, eng.tensor(hy), None if ex is None else eng.tensor(ex), full=True)
+            return K[0, p * m:(p + 1) * m, p * m:(p + 1) * m]
+
+        S1 = block(prob, hyper, extra)
+        Kss = S1[:T, :T].clone()
+        Kn = S1[T:, T:].clone()
+        bare = self._problem(m, nugget=False)
+        bare.extra_kernel, bare.extra_len = _lib.KERNEL_NONE, 0
+        npar = _lib.KERNEL_NPAR[prob.kernel]
+        a1, a2, a3 = (float(v) for v in hyper[0, npar + 3 * p:npar + 3 * p + 3])
+        Ks = (S1 if not prob.extra_len else block(bare, hyper, None))[:T, T:].clone()
+        only_dd = np.array(hyper, dtype=float)
+        only_dd[0, npar:] = 0.0
+        only_dd[0, npar + 3 * p + 1] = 1.0                       # a2 = 1: the block is ddK
+        Ks += 4.0 * a1 * a3 * block(bare, only_dd, None)[:T, T:]
+        if T == N:
+            wn = float(hyper[0, npar - 1])
+            Ks += wn * wn * (a1 + a2 + a3) ** 2 * torch.eye(T, dtype=torch.float64, device=Ks.device)
+        ld, stride = eng.ld(N), eng.matrix_stride(N)
+        Kw = torch.zeros((1, stride // ld, ld), dtype=torch.float64, device=Ks.device)
+        Kw[0, :N, :N] = Kn
+        ll, info = eng.potrf_loglike(Kw, N, eng.tensor(r[None, :]))
+        if int(info[0]) != 0:
+            raise np.linalg.LinAlgError("%d-th leading minor of the array is not positive definite"
+                                        % int(info[0]))
+        z = Kw[0, N, :N]
+        V, _ = eng.solve_logdet(Kw, N, Ks.contiguous(), None, shared=True)
+        y_mean = V @ z
+        y_cov = Kss - V @ V.T
+        y_std = torch.sqrt(torch.diagonal(y_cov))
+        return y_mean.cpu().numpy(), y_std.cpu().numpy(), y_cov.cpu().numpy()
+
     def log_likelihood_batch(self, A, Bm=None, C=None):
         """Rows of ``A`` (B, npar + 3M), extra-kernel rows ``C`` (B, ne + M) when an
         extra kernel is set, mean-parameter rows ``Bm`` when the means take any."""

@@ -60,6 +60,23 @@ def main():
             np.asarray(mean), np.asarray(std), np.asarray(cov)
         cases.append(dict(name=name, kernel="QuasiPeriodic", grid="grid37", model=model,
                           a=hypers["QuasiPeriodic"], b=b, jitter=jit))
+    # SMALLgp.predict_gp (SMALLgp.py:317-368): three series in the order rv, bis, rhk
+    sa = {"QuasiPeriodic": [20.0, 1.1, 23.0, 0.08, 1.3, 0.4, 0.02, 0.9, 0.2, 0.01, 0.7, 0.5, 0.03]}
+    sc = [4.0, 0.05, 0.3, 0.2, 0.4]                      # extra SquaredExponential (l, wn) + 3 amplitudes
+    sb = [0.3, -0.2, 0.01]
+    for extraname, cc in ((None, []), ("SquaredExponential", sc)):
+        for gname in ("grid37", "gridN"):
+            for model in (1, 2, 3):
+                ek = None if extraname is None else getattr(K_, extraname)
+                gp = ref.SMALLgp(K_.QuasiPeriodic, ek, [M_.Constant, None, M_.Linear], t,
+                                 rv, e1, bis, e3, rhk, e2)
+                with contextlib.redirect_stdout(io.StringIO()):
+                    mean, std, cov = gp.predict_gp(grids[gname], sa["QuasiPeriodic"], sb, cc, model=model)
+                name = "small_%s_%s_%d" % (extraname or "noextra", gname, model)
+                arrays[name + "_mean"], arrays[name + "_std"], arrays[name + "_cov"] = \
+                    np.asarray(mean), np.asarray(std), np.asarray(cov)
+                cases.append(dict(name=name, framework="SMALLgp", kernel="QuasiPeriodic", extrakernel=extraname,
+                                  grid=gname, model=model, a=sa["QuasiPeriodic"], b=sb, c=cc))
     np.savez_compressed(os.path.join(HERE, "golden_predict_v1.npz"), **arrays)
     with open(os.path.join(HERE, "golden_predict_v1.json"), "w") as f:
         json.dump(dict(cases=cases, means=["Constant", "Linear", "Constant"]), f, indent=1)

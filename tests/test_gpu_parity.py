@@ -380,8 +380,8 @@ def test_batched_keplerian_and_sine_means(mf, golden):
 
 
 def test_predict_gp_against_reference_golden(mf):
-    """predict_gp against outputs of the unmodified reference
-    (tests/golden/make_golden_predict.py): non-square, square (wn quirk) and on-data grids."""
+    """predict_gp of BIGgp, BIGgpPlusJitt and SMALLgp against outputs of the unmodified
+    reference (tests/golden/make_golden_predict.py): non-square, square (wn quirk) and on-data grids."""
     import json
     import os
     here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -390,11 +390,18 @@ def test_predict_gp_against_reference_golden(mf):
     means = [mf.means.Constant, mf.means.Linear, mf.means.Constant]
     for case in meta["cases"]:
         jit = case.get("jitter")
-        cls = mf.BIGgpPlusJitt.BIGgp if jit else mf.BIGgp.BIGgp
-        gp = cls(getattr(mf.kernels, case["kernel"]), list(means), d["t"], d["rv"], d["rverr"],
-                 d["rhk"], d["sig_rhk"], d["bis"], d["sig_bis"])
-        args = (d[case["grid"]], case["a"], case["b"]) + ((jit,) if jit else ())
-        mean, std, cov = gp.predict_gp(*args, model=case["model"])
+        if case.get("framework") == "SMALLgp":
+            ek = None if case["extrakernel"] is None else getattr(mf.kernels, case["extrakernel"])
+            gp = mf.SMALLgp.SMALLgp(getattr(mf.kernels, case["kernel"]), ek,
+                                    [mf.means.Constant, None, mf.means.Linear], d["t"], d["rv"], d["rverr"],
+                                    d["bis"], d["sig_bis"], d["rhk"], d["sig_rhk"])
+            mean, std, cov = gp.predict_gp(d[case["grid"]], case["a"], case["b"], case["c"], model=case["model"])
+        else:
+            cls = mf.BIGgpPlusJitt.BIGgp if jit else mf.BIGgp.BIGgp
+            gp = cls(getattr(mf.kernels, case["kernel"]), list(means), d["t"], d["rv"], d["rverr"],
+                     d["rhk"], d["sig_rhk"], d["bis"], d["sig_bis"])
+            args = (d[case["grid"]], case["a"], case["b"]) + ((jit,) if jit else ())
+            mean, std, cov = gp.predict_gp(*args, model=case["model"])
         name = case["name"]
         wm, ws, wc = d[name + "_mean"], d[name + "_std"], d[name + "_cov"]
         # measured: mean 2e-13, covariance 7e-13 of max|cov|, std 1e-9 relative (K** - K* K^-1 K*^T
