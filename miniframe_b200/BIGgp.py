@@ -195,13 +195,10 @@ class BIGgp(GPBase):
         reads chunk 2 and mean slot 2, 'bis' chunk 1 and slot 1; the covariance being
         conditioned on carries NO observational errors (only wn^2, and the jitter in PlusJitt);
         when len(time) == len(t) every kernel class adds wn^2 on the diagonal of K* too."""
-        import torch
         if model not in self._MODELS:
             raise UnboundLocalError("model must be 'rv', 'rhk' or 'bis'")   # the reference falls through
         blk, chunk, slot = self._MODELS[model]
-        eng = self.engine
         time = np.asarray(time, dtype=float)
-        T, N = time.size, self.t.size
         self.mean_pars = b
         if self.means[slot] is None:
             raise TypeError("'NoneType' object is not callable")           # BIGgp.py:609 with no mean
@@ -209,6 +206,25 @@ class BIGgp(GPBase):
         mean_val = np.asarray(self.means[slot](time), dtype=float)
         hyper = self._hyper_row(a)
         self._check_finite(hyper)
+        npar = _lib.KERNEL_NPAR[self._kernel_id()]
+        vc, vr, lc, bc, br = (float(v) for v in hyper[0, npar:npar + 5])
+        cw = {0: (vc + vr) ** 2, 1: lc * lc, 2: (bc + br) ** 2}[blk]
+        y_mean, y_cov, info = self._conditional(time, hyper, blk, r, cw, extra_diag)
+        if info != 0:
+            raise np.linalg.LinAlgError("%d-th leading minor of the array is not positive definite"
+                                        % info)                            # scipy cho_factor, uncaught
+        import torch
+        y_mean = y_mean + self.engine.tensor(mean_val)
+        y_std = torch.sqrt(torch.diagonal(y_cov))
+        return y_mean.cpu().numpy(), y_std.cpu().numpy(), y_cov.cpu().numpy()
+
+    def _conditional(self, time, hyper, blk, r, square_wn_coef, extra_diag=0.0):
+        """mean = K* K^-1 r and cov = K** - K* K^-1 K*^T for the covariance of diagonal block
+        ``blk`` under the hyper-parameter row ``hyper``, as device tensors, plus the
+        factorisation status (0 = positive definite)."""
+        import torch
+        eng = self.engine
+        T, N = time.size, self.t.size
         x = np.concatenate([time, np.asarray(self.t, dtype=float)])
         m = x.size
         prob = self._problem(m)
@@ -219,27 +235,72 @@ class BIGgp(GPBase):
         if extra_diag:
             Kss += extra_diag * torch.eye(T, dtype=torch.float64, device=Kss.device)
         if T == N:
-            # square tstar: the four kernel-class calls each add wn^2 I (kernels.py:296)
+            # square tstar: every kernel-class call adds wn^2 I (kernels.py:296)
             npar = _lib.KERNEL_NPAR[self._kernel_id()]
             wn = float(hyper[0, npar - 1])
-            vc, vr, lc, bc, br = (float(v) for v in hyper[0, npar:npar + 5])
-            cw = {0: (vc + vr) ** 2, 1: lc * lc, 2: (bc + br) ** 2}[blk]
-            Ks += cw * wn * wn * torch.eye(T, dtype=torch.float64, device=Ks.device)
+            Ks += square_wn_coef * wn * wn * torch.eye(T, dtype=torch.float64, device=Ks.device)
         ld, stride = eng.ld(N), eng.matrix_stride(N)
         Kw = torch.zeros((1, stride // ld, ld), dtype=torch.float64, device=Ks.device)
         Kw[0, :N, :N] = S[T:, T:]
         if extra_diag:
             Kw[0, :N, :N] += extra_diag * torch.eye(N, dtype=torch.float64, device=Ks.device)
-        ll, info = eng.potrf_loglike(Kw, N, eng.tensor(r[None, :]))
+        ll, info = eng.potrf_loglike(Kw, N, eng.tensor(np.asarray(r, dtype=float)[None, :]))
         if int(info[0]) != 0:
-            raise np.linalg.LinAlgError("%d-th leading minor of the array is not positive definite"
-                                        % int(info[0]))                    # scipy cho_factor, uncaught
+            return None, None, int(info[0])
         z = Kw[0, N, :N]
         V, _ = eng.solve_logdet(Kw, N, Ks, None, shared=True)               # (T, N): rows L^-1 K*_i
-        y_mean = V @ z + eng.tensor(mean_val)
-        y_cov = Kss - V @ V.T
-        y_std = torch.sqrt(torch.diagonal(y_cov))
-        return y_mean.cpu().numpy(), y_std.cpu().numpy(), y_cov.cpu().numpy()
+        return V @ z, Kss - V @ V.T, 0
+
+    def _predict_base(self, time, y, a, scaling, blk):
+        """predict_G / predict_Gdot: condition the bare kernel (or its second derivative) on
+        ``y``.  That matrix is a diagonal block of the device build with unit scaling:
+        k22 with lc = 1 is kernel(x), k11 with (vc, vr) = (0, 1) is ddKdt2dt1(x)."""
+        time = np.asarray(time, dtype=float)
+        hyper = np.array(self._hyper_row(a), dtype=float)
+        self._check_finite(hyper)
+        npar = _lib.KERNEL_NPAR[self._kernel_id()]
+        hyper[0, npar:npar + 5] = scaling
+        mean, cov, info = self._conditional(time, hyper, blk, np.asarray(y, dtype=float), 1.0)
+        if info != 0:
+            print('Not positive definite matrix')          # BIGgp.py:406-408
+            return np.zeros_like(time), 0
+        print('Positive definite matrix')
+        return mean.cpu().numpy(), cov.cpu().numpy()
+
+    def predict_G(self, time, y, a):
+        """Prediction of the latent process G(t) from ``y`` (reference BIGgp.py:381-420)."""
+        return self._predict_base(time, y, a, [0.0, 0.0, 1.0, 0.0, 0.0], 1)
+
+    def predict_Gdot(self, time, y, a):
+        """Prediction of dG/dt from ``y`` with the ddK/dt2dt1 kernel (reference BIGgp.py:423-463)."""
+        return self._predict_base(time, y, a, [0.0, 1.0, 0.0, 0.0, 0.0], 0)
+
+    def predict_rv(self, time, a):
+        """mean, covariance, std for the RVs (reference BIGgp.py:466-492); the reference combines
+        the two predictions LINEARLY in vc, vr (covariance included), and so does this."""
+        mu, cov = self.predict_G(time, self.rv, a)
+        mudot, covdot = self.predict_Gdot(time, self.rv, a)
+        vc, vr, lc, bc, br = self._scaling_pars(a)
+        mean = vc * mu + vr * mudot
+        covariance = vc * cov + vr * covdot
+        return mean, covariance, np.sqrt(np.diag(covariance))
+
+    def predict_rhk(self, time, a):
+        """mean, covariance, std for log R'hk (reference BIGgp.py:495-520)."""
+        mu, cov = self.predict_G(time, self.rhk, a)
+        vc, vr, lc, bc, br = self._scaling_pars(a)
+        mean = lc * mu
+        covariance = lc * cov
+        return mean, covariance, np.sqrt(np.diag(covariance))
+
+    def predict_bis(self, time, a):
+        """mean, covariance, std for the BIS (reference BIGgp.py:523-549)."""
+        mu, cov = self.predict_G(time, self.bis, a)
+        mudot, covdot = self.predict_Gdot(time, self.bis, a)
+        vc, vr, lc, bc, br = self._scaling_pars(a)
+        mean = bc * mu + br * mudot
+        covariance = bc * cov + br * covdot
+        return mean, covariance, np.sqrt(np.diag(covariance))
 
     def predict_gp(self, time, a, b, model='rv'):
         """y_mean, y_std, y_cov of the chosen series at ``time`` (reference BIGgp.py:570-641)."""

@@ -60,6 +60,21 @@ def main():
             np.asarray(mean), np.asarray(std), np.asarray(cov)
         cases.append(dict(name=name, kernel="QuasiPeriodic", grid="grid37", model=model,
                           a=hypers["QuasiPeriodic"], b=b, jitter=jit))
+    # predict_G / predict_Gdot / predict_rv / predict_rhk / predict_bis (BIGgp.py:381-549)
+    for kname, a in hypers.items():
+        for gname in ("grid37", "gridN"):
+            gp = ref.BIGgp(getattr(K_, kname), [None, None, None], ref_shim.as_time(t),
+                           rv, e1, rhk, e2, bis, e3)
+            with contextlib.redirect_stdout(io.StringIO()):
+                outs = {"G": gp.predict_G(grids[gname], rv, a), "Gdot": gp.predict_Gdot(grids[gname], bis, a),
+                        "rv": gp.predict_rv(grids[gname], a), "rhk": gp.predict_rhk(grids[gname], a),
+                        "bis": gp.predict_bis(grids[gname], a)}
+            for what, out in outs.items():
+                name = "base_%s_%s_%s" % (kname, gname, what)
+                for k, v in enumerate(out):
+                    arrays["%s_%d" % (name, k)] = np.asarray(v)
+                cases.append(dict(name=name, framework="base", kernel=kname, grid=gname, what=what, a=a,
+                                  nout=len(out)))
     # SMALLgp.predict_gp (SMALLgp.py:317-368): three series in the order rv, bis, rhk
     sa = {"QuasiPeriodic": [20.0, 1.1, 23.0, 0.08, 1.3, 0.4, 0.02, 0.9, 0.2, 0.01, 0.7, 0.5, 0.03]}
     sc = [4.0, 0.05, 0.3, 0.2, 0.4]                      # extra SquaredExponential (l, wn) + 3 amplitudes
