@@ -217,6 +217,46 @@ def test_cooperative_groups_match_one_cta_per_matrix(mf, monkeypatch, N, G):
     assert np.all(np.isinf(llG[[1, 4]])) and np.all(llG[[1, 4]] < 0)
 
 
+@pytest.mark.parametrize("N", [1, 7, 21, 43, 64, 100, 150, 213])
+def test_small_tile_variant_against_oracle_and_large_tile_variant(mf, monkeypatch, N):
+    """Matrices of order <= 960 in batches larger than the GPU run on 64-row tiles, three CTAs per
+    SM: same factor as the 128-row variant (the per-element operation order does not depend on the
+    tile height), log-likelihoods within 1e-9 of the oracle, failures per sample."""
+    from miniframe_b200._engine import Engine
+    eng = Engine.get()
+    t, (rv, rhk, bis), (e1, e2, e3) = go.synthetic_series(N, seed=N)
+    gp = mf.BIGgp.BIGgp(mf.kernels.SquaredExponential, [None, None, None], t, rv, e1, rhk, e2, bis, e3)
+    n = 3 * N
+    B = 460                                         # more than 3 x 148 CTAs: the persistent loop runs
+    rng = np.random.default_rng(N)
+    A = np.column_stack([rng.uniform(2, 30, B), rng.uniform(0.01, 0.5, B)] + [rng.uniform(0.2, 1.5, B)] * 5)
+    A[5] = A[-2] = [5000.0, 0.0, 1e8, 1e8, 1e8, 1e8, 1e8]          # not positive definite in FP64
+    prob = gp._problem(N)
+    resid = eng.tensor(go.biggp_y(rv, rhk, bis)[None, :])
+    out = {}
+    monkeypatch.setenv("MF_COOP_GROUP", "1")
+    for nmi in ("2", "1"):
+        monkeypatch.setenv("MF_NMI", nmi)
+        Kd = eng.build_cov(prob, eng.tensor(t), eng.tensor(gp._diag_yerr()), eng.tensor(A), None, full=False)
+        ll, info = eng.potrf_loglike(Kd, n, resid)
+        out[nmi] = (Kd.cpu().numpy(), ll.cpu().numpy(), info.cpu().numpy())
+    (K2, ll2, i2), (K1, ll1, i1) = out["2"], out["1"]
+    assert np.array_equal(i1, i2)
+    bad = i1 != 0
+    if N >= 7:
+        assert bad[5] and bad[-2]
+    ok = np.nonzero(~bad)[0]
+    assert ok.size >= B - 8
+    for b in ok[:: max(1, ok.size // 40)]:
+        assert np.array_equal(np.tril(K1[b, :n, :n]), np.tril(K2[b, :n, :n]))
+        assert np.array_equal(K1[b, n, :n], K2[b, n, :n])
+    assert np.array_equal(ll1[ok], ll2[ok]) and np.all(np.isinf(ll1[bad]))
+    y = go.biggp_y(rv, rhk, bis)
+    for b in ok[[0, 1, ok.size // 2, -1]]:
+        want = go.biggp_loglike_literal("SquaredExponential", A[b], t, y, e1, e2, e3)
+        assert rel_err(float(ll1[b]), want) <= LL_RTOL
+
+
 def test_batch_mixes_failures_and_successes(mf, golden):
     """Non-positive-definite samples give -inf for themselves only."""
     d = golden.data("spot40")
