@@ -731,36 +731,47 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
     p.sync = nullptr;
     p.dinv = nullptr;
     p.trace = nullptr;
+    // Tile variant.  Small matrices: 64-row tiles (one 8-row fragment per warp, 80 registers) and
+    // THREE CTAs per SM.  The 64 sequential pivots per block column are a latency chain that only
+    // other resident matrices can hide, and small matrices are mostly that chain; measured (2664
+    // matrices): n = 300 +23 %, n = 600 +13 %, n = 1000 +1 %, n = 1500 -9 %.  MF_NMI = 1 | 2
+    // forces a variant (tests).
+    const char* en = getenv("MF_NMI");
+    const bool small_tiles = (en ? atoi(en) == 1 : n <= 960) && !getenv("MF_DBG");
+    const int tile_rows = small_tiles ? 64 : 128;
+    const int cta_slots = (small_tiles ? 3 : 2) * h->sm_count;
+    const int tile_smem = small_tiles ? pf::smem_bytes(3, 1) : pf::smem_bytes(3);
+    const void* const coop_fn = small_tiles ? (const void*)pf::mf_potrf_ll_kernel<3, 3, 0, 1, 1>
+                                            : (const void*)pf::mf_potrf_ll_kernel<3, 2, 0, 1, 2>;
     {
         // Fewer matrices than CTA slots: several CTAs per matrix, at most one per row tile of the
         // first block column.  MF_COOP_GROUP overrides the choice (1 = never; tests use it).
-        const int ntile0 = (n + 1 + pf::TM - 1) / pf::TM;
-        int G = slots / batch;
+        const int ntile0 = (n + 1 + tile_rows - 1) / tile_rows;
+        int G = cta_slots / batch;
         if (G > ntile0) G = ntile0;
         const char* eg = getenv("MF_COOP_GROUP");
         if (eg) G = atoi(eg);
-        if (G > slots) G = slots;
+        if (G > cta_slots) G = cta_slots;
         if (G > h->coop_groups) G = h->coop_groups;
-        // One CTA per SM instead of two when that still gives every tile of the first block column
-        // its own CTA, or when there is a single matrix: a CTA that has its SM to itself runs a
-        // tile ~1.75x faster than two sharing one, and which CTAs share an SM cannot be chosen.
+        // One CTA per SM when that still gives every tile of the first block column its own CTA,
+        // or when there is a single matrix: a CTA that has its SM to itself runs a tile ~1.75x
+        // faster than two sharing one, and which CTAs share an SM cannot be chosen.
         const int per_sm1 = h->sm_count / batch;          // group size with one CTA per SM
         const bool alone = !eg && per_sm1 >= 2 && (batch == 1 || per_sm1 >= ntile0);
         if (alone) G = per_sm1 < ntile0 ? per_sm1 : ntile0;
         if (G >= 2 && !getenv("MF_DBG")) {
-            int ngroups = (alone ? h->sm_count : slots) / G;
+            int ngroups = (alone ? h->sm_count : cta_slots) / G;
             if (ngroups > batch) ngroups = batch;
+            if (ngroups > h->coop_groups) ngroups = h->coop_groups;
             // a dynamic shared-memory request above half an SM keeps a second CTA off the SM
-            const int smem = alone ? 120 * 1024 : pf::smem_bytes(3);
+            const int smem = alone ? 120 * 1024 : tile_smem;
             p.group = G;
             p.sync = h->coop_sync;
             p.dinv = h->coop_dinv;
             MF_CUDA_CHECK(h, cudaMemsetAsync(h->coop_sync, 0, (size_t)h->coop_groups * 8 * sizeof(unsigned), st));
-            MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<3, 2, 0, 1, 2>,
-                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+            MF_CUDA_CHECK(h, cudaFuncSetAttribute(coop_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
             void* args[] = {(void*)&p};
-            const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)pf::mf_potrf_ll_kernel<3, 2, 0, 1, 2>,
-                                                               dim3(ngroups * G), dim3(pf::THREADS), args,
+            const cudaError_t ce = cudaLaunchCooperativeKernel(coop_fn, dim3(ngroups * G), dim3(pf::THREADS), args,
                                                                smem, st);
             if (ce == cudaSuccess) return MF_OK;
             if (ce != cudaErrorCooperativeLaunchTooLarge) {
@@ -772,6 +783,14 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
             p.group = 1;
         }
     }
+    if (small_tiles) {
+        const int grid1 = batch < cta_slots ? batch : cta_slots;
+        MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<3, 3, 0, 0, 1>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem));
+        pf::mf_potrf_ll_kernel<3, 3, 0, 0, 1><<<grid1, pf::THREADS, tile_smem, st>>>(p);
+        MF_CUDA_CHECK(h, cudaGetLastError());
+        return MF_OK;
+    }
 #define MF_LAUNCH(DBG_)                                                                            \
     do {                                                                                           \
         MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<3, 2, DBG_, 0, 2>,               \
@@ -779,25 +798,6 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
                                               pf::smem_bytes(3)));                                 \
         pf::mf_potrf_ll_kernel<3, 2, DBG_, 0, 2><<<grid, pf::THREADS, pf::smem_bytes(3), st>>>(p);    \
     } while (0)
-    {
-        // Small matrices: 64-row tiles (one 8-row fragment per warp, 80 registers) and THREE
-        // CTAs per SM.  The 64 sequential pivots per block column are a latency chain that only
-        // other resident matrices can hide, and small matrices are mostly that chain; measured
-        // (2664 matrices): n = 300 +23 %, n = 600 +13 %, n = 1000 +1 %, n = 1500 -9 %.
-        // MF_NMI = 1 | 2 forces a variant (tests).
-        const char* en = getenv("MF_NMI");
-        const bool small_tiles = en ? atoi(en) == 1 : n <= 960;
-        if (small_tiles && !getenv("MF_DBG")) {
-            const int slots3 = 3 * h->sm_count;
-            const int grid1 = batch < slots3 ? batch : slots3;
-            MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<3, 3, 0, 0, 1>,
-                                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  pf::smem_bytes(3, 1)));
-            pf::mf_potrf_ll_kernel<3, 3, 0, 0, 1><<<grid1, pf::THREADS, pf::smem_bytes(3, 1), st>>>(p);
-            MF_CUDA_CHECK(h, cudaGetLastError());
-            return MF_OK;
-        }
-    }
     // MF_DBG selects one of the timing-experiment instantiations (scripts/gpu_env_sweep.sh,
     // scripts/trace_run.py); results of those launches are not valid likelihoods
     const char* ed = getenv("MF_DBG");
