@@ -736,8 +736,12 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
     // other resident matrices can hide, and small matrices are mostly that chain; measured (2664
     // matrices): n = 300 +23 %, n = 600 +13 %, n = 1000 +1 %, n = 1500 -9 %.  MF_NMI = 1 | 2
     // forces a variant (tests).
+    // Larger matrices in batches too small to fill the GPU (cooperative regime) also take the
+    // 64-row tiles: twice the tiles to spread over the CTAs of a group (measured: n = 6000, B = 1
+    // 26.1 -> 18.3 ms, n = 30000 643 -> 564 ms; break-even near batch x 128-row-tiles = 2.5 x 296).
     const char* en = getenv("MF_NMI");
-    const bool small_tiles = (en ? atoi(en) == 1 : n <= 960) && !getenv("MF_DBG");
+    const long tiles128 = (long)batch * ((n + 1 + 127) / 128);
+    const bool small_tiles = (en ? atoi(en) == 1 : (n <= 960 || tiles128 < 5L * h->sm_count)) && !getenv("MF_DBG");
     const int tile_rows = small_tiles ? 64 : 128;
     const int cta_slots = (small_tiles ? 3 : 2) * h->sm_count;
     const int tile_smem = small_tiles ? pf::smem_bytes(3, 1) : pf::smem_bytes(3);
