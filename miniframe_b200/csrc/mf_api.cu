@@ -44,7 +44,7 @@ extern "C" int mf_create(mf_handle_t* out, int device) {
         delete h;
         return MF_ERR_CUDA;
     }
-    h->coop_groups = 2 * h->sm_count;
+    h->coop_groups = 3 * h->sm_count;
     h->coop_sync = nullptr;
     h->coop_dinv = nullptr;
     if (cudaMalloc(&h->coop_sync, (size_t)h->coop_groups * 8 * sizeof(unsigned)) != cudaSuccess ||

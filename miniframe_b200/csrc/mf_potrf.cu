@@ -750,21 +750,26 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
     {
         // Fewer matrices than CTA slots: several CTAs per matrix, at most one per row tile of the
         // first block column.  MF_COOP_GROUP overrides the choice (1 = never; tests use it).
+        // (for a handful of large matrices at most two CTAs per SM, also on the small tiles: with
+        // three, one n = 30000 matrix takes 785 ms instead of 500; many small groups do better
+        // with all three: 128 matrices of order 600, 97.5 k -> 111 k evaluations/s)
+        const int coop_slots = batch >= 16 ? cta_slots : 2 * h->sm_count;
         const int ntile0 = (n + 1 + tile_rows - 1) / tile_rows;
-        int G = cta_slots / batch;
+        int G = coop_slots / batch;
         if (G > ntile0) G = ntile0;
         const char* eg = getenv("MF_COOP_GROUP");
         if (eg) G = atoi(eg);
-        if (G > cta_slots) G = cta_slots;
+        if (G > coop_slots) G = coop_slots;
         if (G > h->coop_groups) G = h->coop_groups;
-        // One CTA per SM when that still gives every tile of the first block column its own CTA,
-        // or when there is a single matrix: a CTA that has its SM to itself runs a tile ~1.75x
-        // faster than two sharing one, and which CTAs share an SM cannot be chosen.
+        // One CTA per SM when that still gives every tile of the first block column its own CTA:
+        // a CTA that has its SM to itself runs a tile ~1.75x faster than two sharing one, and
+        // which CTAs share an SM cannot be chosen.  (With more tiles than SMs the shared mode
+        // wins: n = 30000, one matrix, 148 CTAs 567 ms, 296 or 444 CTAs 500 ms.)
         const int per_sm1 = h->sm_count / batch;          // group size with one CTA per SM
-        const bool alone = !eg && per_sm1 >= 2 && (batch == 1 || per_sm1 >= ntile0);
+        const bool alone = !eg && per_sm1 >= 2 && per_sm1 >= ntile0;
         if (alone) G = per_sm1 < ntile0 ? per_sm1 : ntile0;
         if (G >= 2 && !getenv("MF_DBG")) {
-            int ngroups = (alone ? h->sm_count : cta_slots) / G;
+            int ngroups = (alone ? h->sm_count : coop_slots) / G;
             if (ngroups > batch) ngroups = batch;
             if (ngroups > h->coop_groups) ngroups = h->coop_groups;
             // a dynamic shared-memory request above half an SM keeps a second CTA off the SM
