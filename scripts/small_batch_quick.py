@@ -5,7 +5,7 @@ import numpy as np, torch
 from miniframe_b200 import kernels
 from miniframe_b200.BIGgp import BIGgp
 from oracle import gp_oracle as go
-for N, B in [(500, 1), (2000, 1), (2000, 8), (10000, 1), (10000, 2)]:
+for N, B in [(200, 1), (500, 1), (500, 8), (500, 64), (2000, 1), (2000, 8), (10000, 1)]:
     t, (rv, rhk, bis), (e1, e2, e3) = go.synthetic_series(N, seed=1)
     H = torch.as_tensor(go.synthetic_biggp_hypers(B, seed=2), device="cuda")
     gp = BIGgp(kernels.QuasiPeriodic, [None, None, None], t=t, rv=rv, rverr=e1, rhk=rhk, sig_rhk=e2, bis=bis, sig_bis=e3)
