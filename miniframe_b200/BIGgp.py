@@ -179,6 +179,63 @@ class BIGgp(GPBase):
     def minus_log_likelihood(self, a, b, nugget=True):
         return -self.log_likelihood(a, b, nugget=True)
 
+    # ---- sampling (reference BIGgp.py:320-378) --------------------------------------------
+    def _draw(self, K, n, size, seed):
+        """x = L xi with K = L L^T from the factorisation kernel and xi ~ N(0, I) drawn on the
+        device.  The reference draws with scipy's multivariate_normal (eigen-decomposition, numpy's
+        global generator): the same distribution, not the same numbers."""
+        import torch
+        eng = self.engine
+        ll, info = eng.potrf_loglike(K, n, None)
+        if int(info[0]) != 0:
+            raise np.linalg.LinAlgError("the covariance is not positive definite in FP64 "
+                                        "(pivot %d)" % int(info[0]))
+        L = torch.tril(K[0, :n, :n])
+        gen = torch.Generator(device=L.device)
+        if seed is None:
+            gen.seed()
+        else:
+            gen.manual_seed(int(seed))
+        xi = torch.randn((n, 1 if size is None else int(size)), generator=gen, dtype=torch.float64, device=L.device)
+        x = (L @ xi).T.cpu().numpy()
+        return x[0] if size is None else x
+
+    def _workspace_copy(self, S, n):
+        import torch
+        eng = self.engine
+        ld, stride = eng.ld(n), eng.matrix_stride(n)
+        Kw = torch.zeros((1, stride // ld, ld), dtype=torch.float64, device=S.device)
+        Kw[0, :n, :n] = S
+        return Kw
+
+    def sample(self, a, size=None, seed=None):
+        """Draw from N(0, K) with K = compute_matrix(a) (reference BIGgp.py:320-334)."""
+        eng = self.engine
+        _, make = self._diag(True)
+        n = 3 * self.t.size
+        K = eng.build_cov(self._problem(self.t.size), eng.tensor(np.asarray(self.t, dtype=float)),
+                          eng.tensor(make()), eng.tensor(self._hyper_row(a)), None, full=False)
+        return self._draw(K, n, size, seed)
+
+    def _sample_base(self, a, scaling, blk, size, seed):
+        eng = self.engine
+        N = self.t.size
+        hyper = np.array(self._hyper_row(a), dtype=float)
+        npar = _lib.KERNEL_NPAR[self._kernel_id()]
+        hyper[0, npar:npar + 5] = scaling
+        Kbig = eng.build_cov(self._problem(N), eng.tensor(np.asarray(self.t, dtype=float)),
+                             eng.tensor(np.zeros(3 * N)), eng.tensor(hyper), None, full=True)
+        S = Kbig[0, blk * N:(blk + 1) * N, blk * N:(blk + 1) * N]
+        return self._draw(self._workspace_copy(S, N), N, size, seed)
+
+    def sample_from_G(self, a, size=None, seed=None):
+        """Draw from the latent process G(t) at the observation times (reference BIGgp.py:339-357)."""
+        return self._sample_base(a, [0.0, 0.0, 1.0, 0.0, 0.0], 1, size, seed)
+
+    def sample_from_Gdot(self, a, size=None, seed=None):
+        """Draw from dG/dt at the observation times (reference BIGgp.py:360-378)."""
+        return self._sample_base(a, [0.0, 1.0, 0.0, 0.0, 0.0], 0, size, seed)
+
     # ---- prediction (SURVEY section 8 f1) -----------------------------------------------
     _MODELS = {"rv": (0, 0, 0), "rhk": (1, 2, 2), "bis": (2, 1, 1)}   # block, chunk of y, mean slot
 

@@ -40,6 +40,20 @@ class BIGgp(_plain.BIGgp):
             raise TypeError("log_likelihood() missing 1 required positional argument: 'c'")
         return -self.log_likelihood(a, b, c, nugget=True)
 
+    def sample(self, a, j=None, size=None, seed=None):
+        """Draw from N(0, compute_matrix(a, j)).  The reference's sample(a) forwards only ``a`` to
+        compute_matrix(a, j) and so raises TypeError (BIGgpPlusJitt.py:326-341); the same happens
+        here unless the jitters are given."""
+        if j is None:
+            raise TypeError("compute_matrix() missing 1 required positional argument: 'j'")
+        eng = self.engine
+        _, make = self._diag(True)
+        n = 3 * self.t.size
+        K = eng.build_cov(self._problem(self.t.size, jitter=True), eng.tensor(np.asarray(self.t, dtype=float)),
+                          eng.tensor(make()), eng.tensor(self._hyper_row(a)),
+                          eng.tensor(np.asarray(j, dtype=float).ravel()[None, :3]), full=False)
+        return self._draw(K, n, size, seed)
+
     def predict_gp(self, time, a, b, c, model='rv'):
         """As BIGgp.predict_gp with the series' jitter^2 added to the covariance being conditioned
         on and to K** (BIGgpPlusJitt.py:576-653).  The jitters are read in the order of y,

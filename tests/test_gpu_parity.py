@@ -475,3 +475,33 @@ def test_predict_gp_against_reference_golden(mf):
         assert np.abs(cov - wc).max() <= 1e-10 * scale, name
         ok = np.isfinite(ws) & (ws > 1e-4 * np.sqrt(scale))
         assert np.allclose(std[ok], ws[ok], rtol=1e-7, atol=0), name
+
+
+def test_samples_have_the_covariance_they_are_drawn_from(mf):
+    """sample / sample_from_G / sample_from_Gdot (reference BIGgp.py:320-378): the reference draws
+    with scipy + numpy's global generator, so only the distribution can be compared."""
+    N = 14
+    t, (rv, rhk, bis), (e1, e2, e3) = go.synthetic_series(N, seed=2)
+    gp = mf.BIGgp.BIGgp(mf.kernels.QuasiPeriodic, [None, None, None], t, rv, e1, rhk, e2, bis, e3)
+    a = [20.0, 1.1, 23.0, 0.3, 1.3, 0.4, 0.9, 0.7, 0.5]
+    draws = 20000
+    for what, K in (("sample", gp.compute_matrix(a)), ("sample_from_G", None), ("sample_from_Gdot", None)):
+        X = getattr(gp, what)(a, size=draws, seed=5)
+        if what == "sample_from_G":
+            K = mf.kernels.QuasiPeriodic(*a[:4])(t[:, None] - t[None, :])
+        if what == "sample_from_Gdot":
+            dd = mf.kernels.QuasiPeriodic.__subclasses__()[2]
+            K = dd(*a[:4])(t[:, None] - t[None, :])
+        assert X.shape == (draws, K.shape[0])
+        C = X.T @ X / draws
+        scale = np.abs(K).max()
+        assert np.abs(C - K).max() <= 6.0 * scale * np.sqrt(2.0 / draws)
+        assert np.abs(X.mean(axis=0)).max() <= 5.0 * np.sqrt(scale / draws)
+        one = getattr(gp, what)(a, seed=5)
+        assert one.shape == (K.shape[0],) and np.array_equal(one, getattr(gp, what)(a, seed=5))
+    gj = mf.BIGgpPlusJitt.BIGgp(mf.kernels.QuasiPeriodic, [None, None, None], t, rv, e1, rhk, e2, bis, e3)
+    with pytest.raises(TypeError):
+        gj.sample(a)
+    Xj = gj.sample(a, [0.5, 0.2, 0.3], size=draws, seed=1)
+    Kj = gj.compute_matrix(a, [0.5, 0.2, 0.3])
+    assert np.abs(Xj.T @ Xj / draws - Kj).max() <= 6.0 * np.abs(Kj).max() * np.sqrt(2.0 / draws)
