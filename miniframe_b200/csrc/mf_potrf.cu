@@ -68,6 +68,7 @@ struct Params {
     unsigned* sync;       // [0] barrier arrivals, [1] diagonal-block sequence number, [2] failed matrix
                           // ordinal + 1, [3] info of the failure
     double* dinv;
+    int* counter;         // next matrix to hand out (one CTA per matrix, zeroed before the launch)
     long long* trace;     // DBG & 16: per-tile phase timestamps of the first matrix of each CTA
 };
 
@@ -201,7 +202,18 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
         __syncthreads();
     };
 
-    for (int mat = grp; mat < p.batch; mat += ngroups, ++ordinal) {
+    // One CTA per matrix: the matrices are handed out through an atomic counter rather than by
+    // striding, so a CTA that gets ahead of its neighbour on the SM simply takes more of them and
+    // all CTAs finish together.  (Cooperative groups and the timing-experiment builds stride.)
+    constexpr bool DYNAMIC = !COOP && DBG == 0;
+    int* const next_mat = reinterpret_cast<int*>(red + 16);
+    for (int mat = grp;; mat += ngroups, ++ordinal) {
+        if (DYNAMIC) {
+            if (tid == 0) *next_mat = atomicAdd(p.counter, 1);
+            __syncthreads();
+            mat = *next_mat;
+        }
+        if (mat >= p.batch) break;
         double* const Kb = p.K + (size_t)mat * p.stride;
         const double* const rb = p.resid ? p.resid + (size_t)mat * p.resid_stride : nullptr;
         int fail = 0;
@@ -731,6 +743,7 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
     p.sync = nullptr;
     p.dinv = nullptr;
     p.trace = nullptr;
+    p.counter = reinterpret_cast<int*>(h->coop_sync);
     // Tile variant.  Small matrices: 64-row tiles (one 8-row fragment per warp, 80 registers) and
     // THREE CTAs per SM.  The 64 sequential pivots per block column are a latency chain that only
     // other resident matrices can hide, and small matrices are mostly that chain; measured (2664
@@ -792,6 +805,7 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
             p.group = 1;
         }
     }
+    MF_CUDA_CHECK(h, cudaMemsetAsync(h->coop_sync, 0, sizeof(int), st));      // p.counter
     if (small_tiles) {
         const int grid1 = batch < cta_slots ? batch : cta_slots;
         MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<3, 3, 0, 0, 1>,
