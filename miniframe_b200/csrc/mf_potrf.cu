@@ -5,18 +5,20 @@
 //
 // Design (B200: 148 SMs, FP64 DMMA, 126 MB L2, HBM3e):
 //   * one matrix per CTA, two CTAs resident per SM (three, on 64-row tiles, for matrices
-//     of order <= 960), persistent over the batch: no inter-CTA synchronisation; the
-//     serial diagonal-block phases of one CTA are hidden behind the other CTAs'
-//     tensor-core work;
+//     of order <= 960), persistent over the batch with the matrices handed out through an
+//     atomic counter: no inter-CTA synchronisation; the serial diagonal-block phases of
+//     one CTA are hidden behind the other CTAs' tensor-core work.  Batches smaller than
+//     the GPU: several CTAs per matrix (COOP, see the kernel's comment);
 //   * LEFT-looking by 64-wide block columns: tile C(128 x 64) = K - L_left L_top^T
 //     is a dense contraction over the already-final columns, accumulated in
 //     registers with mma.sync m8n8k4 f64 (SASS DMMA.8x8x4).  The operands stream
 //     through a 3-stage shared-memory ring fed by TMA (cp.async.bulk.tensor.5d,
-//     SASS UTMALDG.5D, 128-byte hardware swizzle) issued by one elected thread and
-//     synchronised with mbarriers only - no CTA-wide barrier inside the loop.
+//     SASS UTMALDG.5D, 128-byte hardware swizzle): every warp waits on the stage's
+//     mbarrier, and the last warp to release a stage refills it - no CTA-wide barrier
+//     and no producer wait inside the loop.
 //     Every tile of K is read once and every tile of L written once (HBM traffic
 //     ~ n^3/(6*64)*8 B per matrix, arithmetic intensity 16 flop/B);
-//   * each warp owns 16 complete rows (16 x 64 accumulators), so the triangular
+//   * each warp owns complete rows (two 8-row fragments x 64 columns), so the triangular
 //     solve against the diagonal block runs entirely in registers on the tensor
 //     cores: the C-fragment layout (row g, columns 2t, 2t+1) is reused directly as
 //     the A operand with the k index permuted, the matching B operand being one
@@ -44,7 +46,7 @@ constexpr int AW_LD = 65;
 constexpr int SZ_LD = 36 * 64 * 8;
 constexpr int SZ_DINV = 8 * 64 * 8;                  // minus-inverses of the 8 diagonal 8x8 blocks
 constexpr int SZ_COL = 2 * 72 * 8;                   // double-buffered pivot column: 64 values + status word
-constexpr int SZ_RED = 64 * 8;                       // reduction scratch + 2 x NSTAGE mbarriers
+constexpr int SZ_RED = 64 * 8;                       // reduction scratch, next-matrix word, mbarriers, release counters
 constexpr int smem_bytes(int nstage, int nmi = 2) { return nstage * (64 * nmi + NB) * KC * 8 + SZ_LD + SZ_DINV + SZ_COL + SZ_RED + 1024; }
 static_assert(NB * AW_LD * 8 <= 3 * (64 + NB) * KC * 8, "potf2 staging array must fit in the stage area");
 // 128-row tiles (NMI = 2): 3 stages, 97,792 B, two CTAs per SM; 64-row tiles (NMI = 1): 73,216 B, three
