@@ -99,12 +99,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // one 64-row x 16-column box of matrix `mat`, rows 8 * blk8 .., columns c0 ..; lands 128B-swizzled
-__device__ __forceinline__ void tma_box(uint32_t dst, const CUtensorMap* tm, int c0, int blk8, int mat, uint32_t bar) {
+__device__ __forceinline__ void tma_box(uint32_t dst, const CUtensorMap* tm, int c0, int blk8, int mat, uint32_t bar,
+                                        uint64_t policy) {
     asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-        "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-        ::"r"(dst), "l"(tm), "r"(c0), "r"(0), "r"(0), "r"(blk8), "r"(mat), "r"(bar)
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%2, %3, %4, %5, %6}], [%7], %8;"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(0), "r"(0), "r"(blk8), "r"(mat), "r"(bar), "l"(policy)
         : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
     unsigned v;
@@ -286,9 +297,11 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                     const uint32_t dst = stage_u32 + st * STAGE_BYTES;
                     mbar_expect_tx(bar, STAGE_BYTES);
                     const int lmat = (DBG & 256) ? (mat & 3) : mat;
-                    tma_box(dst, &p.tmap, kc * KC, r0 >> 3, lmat, bar);
-                    if (NMI == 2) tma_box(dst + 8192, &p.tmap, kc * KC, (r0 >> 3) + 8, lmat, bar);
-                    tma_box(dst + 8192 * NMI, &p.tmap, kc * KC, j0 >> 3, lmat, bar);
+                    // the rows of the tile are streamed once, the block column's own rows are read
+                    // again by every tile of the block column: tell L2 which to keep
+                    tma_box(dst, &p.tmap, kc * KC, r0 >> 3, lmat, bar, l2_policy_evict_first());
+                    if (NMI == 2) tma_box(dst + 8192, &p.tmap, kc * KC, (r0 >> 3) + 8, lmat, bar, l2_policy_evict_first());
+                    tma_box(dst + 8192 * NMI, &p.tmap, kc * KC, j0 >> 3, lmat, bar, l2_policy_evict_last());
                 };
                 // The warp has consumed chunk kc (stage use_s).  The LAST of the eight warps to
                 // say so refills the stage at once with the chunk NSTAGE further on - of this tile,
