@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per matrix of order 1500, from the ncu capture of
 # one 296-matrix launch (profiles/r1_summary.md section 3)
-NCU_POTRF_BYTES_PER_EVAL = (34.477252e9 + 2.788953e9) / 296
+NCU_POTRF_BYTES_PER_EVAL = (32.052291e9 + 2.783408e9) / 296
 NCU_BUILD_BYTES_PER_EVAL = (0.012423e9 + 2.647412e9) / 296
 
 METRIC = "gp_loglike_evals_per_s"

@@ -9,7 +9,7 @@ for lib in main alt; do
   python - <<PY
 import json
 d=json.load(open('gpurun_out/bench_ab.json'))
-print("rep $rep $lib: potrf ms %.2f (%.2f TF/s) value %.0f power %s" % (d['roofline']['ms_per_launch'], d['roofline']['achieved'], d['value'], d['clocks']['power_w_max']))
+print("rep $rep $lib: build ms %.3f potrf ms %.2f (%.2f TF/s) value %.0f power %s" % (d["roofline_build"]["ms_per_launch"], d['roofline']['ms_per_launch'], d['roofline']['achieved'], d['value'], d['clocks']['power_w_max']))
 PY
 done
 done
