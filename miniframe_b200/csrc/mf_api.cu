@@ -95,9 +95,9 @@ extern "C" int mf_loglike(mf_handle_t h, const mf_problem_t* prob, int batch, co
     const size_t per = (size_t)stride * sizeof(double);
     size_t cap = ws_bytes / per;
     if (cap == 0) MF_FAIL(h, MF_ERR_WORKSPACE, "workspace holds no matrix: need %zu bytes per sample", per);
-    // the factorisation keeps two matrices in flight per SM (three for n <= 960): cut chunks at
+    // the factorisation keeps two matrices in flight per SM (three for n <= 1100): cut chunks at
     // whole waves
-    const size_t wave = (n <= 960 ? 3 : 2) * (size_t)h->sm_count;
+    const size_t wave = (n <= 1100 ? 3 : 2) * (size_t)h->sm_count;
     if (cap > wave && (size_t)batch > cap) cap = cap / wave * wave;
     if (((uintptr_t)workspace & 15) != 0) MF_FAIL(h, MF_ERR_INVALID, "workspace must be 16-byte aligned");
     double* K = static_cast<double*>(workspace);

@@ -5,7 +5,7 @@
 //
 // Design (B200: 148 SMs, FP64 DMMA, 126 MB L2, HBM3e):
 //   * one matrix per CTA, two CTAs resident per SM (three, on 64-row tiles, for matrices
-//     of order <= 960), persistent over the batch with the matrices handed out through an
+//     of order <= 1100), persistent over the batch with the matrices handed out through an
 //     atomic counter: no inter-CTA synchronisation; the serial diagonal-block phases of
 //     one CTA are hidden behind the other CTAs' tensor-core work.  Batches smaller than
 //     the GPU: several CTAs per matrix (COOP, see the kernel's comment);
@@ -762,14 +762,14 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
     // Tile variant.  Small matrices: 64-row tiles (one 8-row fragment per warp, 80 registers) and
     // THREE CTAs per SM.  The 64 sequential pivots per block column are a latency chain that only
     // other resident matrices can hide, and small matrices are mostly that chain; measured (2664
-    // matrices): n = 300 +23 %, n = 600 +13 %, n = 1000 +1 %, n = 1500 -9 %.  MF_NMI = 1 | 2
+    // matrices): n = 300 +23 %, n = 600 +13 %, n = 1100 +1.5 %, n = 1200 -4.6 %, n = 1500 -9 %.  MF_NMI = 1 | 2
     // forces a variant (tests).
     // Larger matrices in batches too small to fill the GPU (cooperative regime) also take the
     // 64-row tiles: twice the tiles to spread over the CTAs of a group (measured: n = 6000, B = 1
     // 26.1 -> 18.3 ms, n = 30000 643 -> 564 ms; break-even near batch x 128-row-tiles = 2.5 x 296).
     const char* en = getenv("MF_NMI");
     const long tiles128 = (long)batch * ((n + 1 + 127) / 128);
-    const bool small_tiles = (en ? atoi(en) == 1 : (n <= 960 || tiles128 < 5L * h->sm_count)) && !getenv("MF_DBG");
+    const bool small_tiles = (en ? atoi(en) == 1 : (n <= 1100 || tiles128 < 5L * h->sm_count)) && !getenv("MF_DBG");
     const int tile_rows = small_tiles ? 64 : 128;
     const int cta_slots = (small_tiles ? 3 : 2) * h->sm_count;
     const int tile_smem = small_tiles ? pf::smem_bytes(3, 1) : pf::smem_bytes(3);

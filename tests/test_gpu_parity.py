@@ -219,7 +219,7 @@ def test_cooperative_groups_match_one_cta_per_matrix(mf, monkeypatch, N, G):
 
 @pytest.mark.parametrize("N", [1, 7, 21, 43, 64, 100, 150, 213])
 def test_small_tile_variant_against_oracle_and_large_tile_variant(mf, monkeypatch, N):
-    """Matrices of order <= 960 in batches larger than the GPU run on 64-row tiles, three CTAs per
+    """Matrices of order <= 1100 in batches larger than the GPU run on 64-row tiles, three CTAs per
     SM: same factor as the 128-row variant (the per-element operation order does not depend on the
     tile height), log-likelihoods within 1e-9 of the oracle, failures per sample."""
     from miniframe_b200._engine import Engine
