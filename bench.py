@@ -8,7 +8,11 @@ N = 500 epochs, QuasiPeriodic kernel), on N GPUs of one box.
 A "step" is one pass of the hot path (covariance build -> Cholesky -> solve ->
 log-det -> log-likelihood) over one batch of 4096 synthetic hyper-parameter sets
 per GPU (weak scaling: every rank evaluates its own 4096; the per-sample results
-are all-gathered over NCCL inside the timed region).  One JSON line on stdout.
+are all-gathered over NCCL inside the timed region).  With N > 1 the line also
+carries "strong": the global batch of BASELINE configs[2] (4096, and 32768) cut
+across the N ranks by the product's own sharded entry point
+(miniframe_b200.dist.log_likelihood_batch_sharded), with rank 0 evaluating the
+same batch alone in the same run as the 1-GPU reference.  One JSON line on stdout.
 """
 import argparse
 import json
@@ -24,10 +28,32 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum per matrix of order 1500, from the ncu capture of
-# one 296-matrix launch (profiles/r1_summary.md section 3)
-NCU_POTRF_BYTES_PER_EVAL = (32.052291e9 + 2.783408e9) / 296
-NCU_BUILD_BYTES_PER_EVAL = (0.012423e9 + 2.647412e9) / 296
+import hashlib
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch come from a tracked ncu capture
+# (profiles/ncu_traffic.json, written by scripts/ncu_to_traffic.py from the raw export of an
+# `ncu --set full` run).  Each entry records the sha256 of the kernel's source file at capture
+# time; when the source has changed since, the figure is stale and `traffic` is reported as null.
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+
+
+def ncu_traffic(kernel_key, n, evals):
+    """(GB per launch of `evals` matrices, note) or (None, why)."""
+    try:
+        with open(TRAFFIC_FILE) as f:
+            table = json.load(f)
+        ent = table[kernel_key]
+        with open(os.path.join(ROOT, ent["source"]), "rb") as f:
+            sha = hashlib.sha256(f.read()).hexdigest()
+        if sha != ent["source_sha256"]:
+            return None, "stale: %s changed since the ncu capture %s" % (ent["source"], ent["capture"])
+        if int(ent["matrix_order"]) != int(n):
+            return None, "captured at n = %d, this run is n = %d" % (ent["matrix_order"], n)
+        per_eval = (ent["dram_bytes_read"] + ent["dram_bytes_write"]) / ent["matrices"]
+        return per_eval * evals / 1e9, ("GB per launch: ncu dram read+write of a %d-matrix launch (%s), "
+                                        "scaled to this launch" % (ent["matrices"], ent["capture"]))
+    except Exception as e:                      # no capture tracked yet
+        return None, "no tracked ncu capture (%s)" % type(e).__name__
 
 METRIC = "gp_loglike_evals_per_s"
 UNIT = "evals/s"
@@ -111,32 +137,49 @@ class ClockSampler(object):
 _WORK = {}
 
 
+def reference_kind():
+    """"reference": the unmodified reference classes can be imported (from /root/reference in the
+    build container, else from the copy oracle/make_ref.py staged under oracle/_ref/);
+    "port": only the oracle's literal port of them is available."""
+    from oracle import ref_shim
+    return "reference" if ref_shim.available() else "port"
+
+
 def _worker_init(N, seed):
     """Pool worker: one BLAS thread each (the pool supplies the parallelism, as emcee's
     `threads=` pool does in the reference, examples/BIGgp_mcmc.py:88)."""
     from oracle import gp_oracle as go          # loads numpy's and scipy's BLAS ...
+    from oracle import ref_shim
     try:
         from threadpoolctl import threadpool_limits
         _WORK["limit"] = threadpool_limits(limits=1)      # ... which are then pinned to 1 thread
     except Exception:
         pass
     t, (rv, rhk, bis), (e1, e2, e3) = go.synthetic_series(N, seed=seed)
-    _WORK.update(go=go, t=t, y=go.biggp_y(rv, rhk, bis), errs=(e1, e2, e3))
+    _WORK.update(go=go, t=t, y=go.biggp_y(rv, rhk, bis), errs=(e1, e2, e3), gp=None)
+    if ref_shim.available():
+        ref = ref_shim.load()                   # the reference's own BIGgp, unmodified
+        _WORK["gp"] = ref.BIGgp(ref.kernels.QuasiPeriodic, [None, None, None], ref_shim.as_time(t),
+                                rv, e1, rhk, e2, bis, e3)
 
 
 def _worker_eval(rows):
+    if _WORK["gp"] is not None:
+        return [float(_WORK["gp"].log_likelihood(list(a), [])) for a in rows]
     go, t, y, (e1, e2, e3) = _WORK["go"], _WORK["t"], _WORK["y"], _WORK["errs"]
     return [go.biggp_loglike_literal("QuasiPeriodic", a, t, y, e1, e2, e3) for a in rows]
 
 
 class CpuPort(object):
-    """The oracle's literal port of the reference's CPU path (17 N x N kernel-class
-    evaluations + scipy cho_factor / cho_solve per likelihood) on every host core: a pool
-    of single-threaded workers, one likelihood per task."""
+    """The reference's CPU path (17 N x N kernel-class evaluations + scipy cho_factor / cho_solve
+    per likelihood) on every host core: a pool of single-threaded workers, one likelihood per
+    task.  The workers call the reference's own BIGgp.log_likelihood when its package is
+    present (reference_kind() == "reference"), else the oracle's literal port of it."""
 
     def __init__(self, N, seed=1):
         import multiprocessing as mp
         self.cores = os.cpu_count() or 1
+        self.kind = reference_kind()
         self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_worker_init, initargs=(N, seed))
 
     def evaluate(self, H):
@@ -150,7 +193,7 @@ class CpuPort(object):
 
 
 def cpu_port_evals(N, H, seconds, max_evals):
-    """Returns (evals/s, evals done, values, cores) for a bounded sample of H."""
+    """Returns (evals/s, evals done, values, cores, kind) for a bounded sample of H."""
     port = CpuPort(N)
     try:
         port.evaluate(H[:port.cores])                      # worker start-up, not timed
@@ -162,16 +205,16 @@ def cpu_port_evals(N, H, seconds, max_evals):
         t0 = time.perf_counter()
         vals = port.evaluate(sample)
         dt = time.perf_counter() - t0
-        return len(vals) / dt, len(vals), vals, port.cores
+        return len(vals) / dt, len(vals), vals, port.cores, port.kind
     finally:
         port.close()
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path.  The
-    reference is pure Python and /root/reference does not travel to the GPU box, so
-    this arm times the oracle's literal port of it (oracle/gp_oracle.py) on all host
-    cores, a bounded sample of the same workload per step."""
+    """--impl reference: the reference's own CPU implementation of the path on all host
+    cores, a bounded sample of the same workload per step: the unmodified reference classes
+    (staged under oracle/_ref/ by oracle/make_ref.py) when present, else the oracle's literal
+    port of them (oracle/gp_oracle.py)."""
     if rank != 0:
         return
     N, t, ys, errs, H = workload(args, 0)
@@ -190,7 +233,7 @@ def run_reference(args, rank, world):
         for k in range(args.steps):
             step(args.warmup + k)
         dt = time.perf_counter() - t0
-        cores = port.cores
+        cores, kind = port.cores, port.kind
     finally:
         port.close()
     value = sample * args.steps / dt
@@ -198,10 +241,12 @@ def run_reference(args, rank, world):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config_dict(args, world),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                              "sample": "%d of the %d hyper-parameter sets per step (pool of %d "
-                                       "single-threaded workers, numpy %s + scipy LAPACK)"
-                                       % (sample, args.batch, cores, np.__version__)},
+                                       "single-threaded workers calling %s, numpy %s + scipy LAPACK)"
+                                       % (sample, args.batch, cores,
+                                          "the reference's BIGgp.log_likelihood" if kind == "reference"
+                                          else "the oracle's literal port", np.__version__)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -232,9 +277,12 @@ def run_ours(args, rank, local_rank, world):
             os.dup2(saved, 1)
             os.close(saved)
 
+    from miniframe_b200 import _lib as mflib
+    from miniframe_b200 import dist as mfdist
     from miniframe_b200 import kernels
     from miniframe_b200.BIGgp import BIGgp
     from miniframe_b200._engine import Engine
+    from oracle import gp_oracle as go      # synthetic input generator only (seeded draws)
     eng = Engine.get()
     lib = eng.lib
 
@@ -254,6 +302,7 @@ def run_ours(args, rank, local_rank, world):
     ld, stride = eng.ld(n), eng.matrix_stride(n)
     chunk = max(1, min(B, ws_bytes // (stride * 8)))
     stream = eng.stream()
+    handle = eng.handle
 
     # ---- FP64 roofline denominators, measured here --------------------------------
     peaks = {}
@@ -270,34 +319,41 @@ def run_ours(args, rank, local_rank, world):
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1_))
         peaks["cublas_dgemm_4096_tflops"] = 2 * 4096 ** 3 / (best * 1e-3) / 1e12
-        # short bursts, best of three: the register probe timed for ~25 ms is clocked down by the
-        # power manager (29.7 TFLOP/s), a ~5 ms burst shows the pipe's rate (37.1)
+        # burst: ~5 ms launches, best of three (the pipe's rate); sustained: the same register
+        # probe run for as long as one factorisation launch of this bench (~150 ms), where the
+        # power manager has settled - the figure a kernel timed inside a long step can reach
         peaks["dmma_probe_tflops"] = max(eng.probe_fp64(0, 4000) for _ in range(3))
         peaks["dfma_probe_tflops"] = max(eng.probe_fp64(1, 4000) for _ in range(3))
+        peaks["dmma_probe_sustained_tflops"] = eng.probe_fp64(0, 120000)
         del a, b
 
     launches = [0]
+    ptr = ctypes.c_void_p
 
     def step(events=None):
+        """One pass over this rank's batch through the C ABI, inputs resident in HBM: covariance
+        build (epoch-interleaved order), residual rows, factorisation + solve + log-det."""
         for b0 in range(0, B, chunk):
             nb = min(chunk, B - b0)
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if events is not None else None
             if ev:
                 ev[0].record()
-            st = lib.mf_build_cov(eng.handle, ctypes.byref(prob), nb, eng.ptr(t_d), eng.ptr(diag_d),
-                                  ctypes.c_void_p(hyper_d.data_ptr() + b0 * prob.hyper_len * 8), None, 0,
-                                  eng.ptr(ws), ld, stride, stream)
-            assert st == 0, lib.mf_last_error(eng.handle)
+            st = lib.mf_build_cov(handle, ctypes.byref(prob), nb, eng.ptr(t_d), eng.ptr(diag_d),
+                                  ptr(hyper_d.data_ptr() + b0 * prob.hyper_len * 8), None,
+                                  mflib.COV_LOWER_INTERLEAVED, eng.ptr(ws), ld, stride, stream)
+            assert st == 0, lib.mf_last_error(handle)
             if ev:
                 ev[1].record()
-            st = lib.mf_potrf_loglike(eng.handle, nb, n, eng.ptr(ws), ld, stride, eng.ptr(resid_d), 0,
-                                      ctypes.c_void_p(ll_d.data_ptr() + b0 * 8),
-                                      ctypes.c_void_p(info_d.data_ptr() + b0 * 4), stream)
-            assert st == 0, lib.mf_last_error(eng.handle)
+            row_n = ptr(ws.data_ptr() + n * ld * 8)
+            st = lib.mf_interleave_resid(handle, nb, 3, N, eng.ptr(resid_d), 0, row_n, stride, stream)
+            assert st == 0, lib.mf_last_error(handle)
+            st = lib.mf_potrf_loglike(handle, nb, n, eng.ptr(ws), ld, stride, row_n, stride,
+                                      ptr(ll_d.data_ptr() + b0 * 8), ptr(info_d.data_ptr() + b0 * 4), stream)
+            assert st == 0, lib.mf_last_error(handle)
             if ev:
                 ev[2].record()
                 events.append(ev)
-            launches[0] += 2
+            launches[0] += 3
         if world > 1:
             dist.all_gather_into_tensor(ll_all, ll_d)
 
@@ -306,6 +362,12 @@ def run_ours(args, rank, local_rank, world):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        tt = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
 
     for _ in range(args.warmup):
         step()
@@ -320,11 +382,7 @@ def run_ours(args, rank, local_rank, world):
     ev_b.record()
     barrier()
     clocks = sampler.stop() if sampler else None
-    elapsed_ms = ev_a.elapsed_time(ev_b)
-    tt = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(tt.item())
+    elapsed_ms = max_over_ranks(ev_a.elapsed_time(ev_b))
     value = world * B * args.steps / (elapsed_ms * 1e-3)
     build_ms = sum(ev[0].elapsed_time(ev[1]) for ev in events) / len(events)
     potrf_ms = sum(ev[1].elapsed_time(ev[2]) for ev in events) / len(events)
@@ -332,17 +390,18 @@ def run_ours(args, rank, local_rank, world):
     gpu_launches = launches[0]
 
     # ---- end to end through the public API, host buffers -------------------------------
-    A_host = torch.from_numpy(np.ascontiguousarray(H)).pin_memory()
+    # N = 1: BIGgp.log_likelihood_batch(host array).  N > 1: the product's sharded entry point,
+    # every rank handing in the same global batch of 4096 * N rows from host memory.
+    H_global = H if world == 1 else np.concatenate([go.synthetic_biggp_hypers(B, seed=1 + r) for r in range(world)])
+    A_host = torch.from_numpy(np.ascontiguousarray(H_global)).pin_memory()
     out_host = torch.empty(B * world, dtype=torch.float64).pin_memory()
-    resid_bytes = gp.y.nbytes
 
     def e2e_step():
-        ll = gp.log_likelihood_batch(A_host)          # H2D of the hyper-parameters inside
         if world > 1:
-            dist.all_gather_into_tensor(ll_all, ll)
-            out_host.copy_(ll_all, non_blocking=False)
+            ll = mfdist.log_likelihood_batch_sharded(gp, A_host)     # H2D of this rank's shard inside
         else:
-            out_host.copy_(ll, non_blocking=False)    # D2H of the result
+            ll = gp.log_likelihood_batch(A_host)                      # H2D of the hyper-parameters inside
+        out_host.copy_(ll, non_blocking=False)                         # D2H of the result
 
     for _ in range(min(args.warmup, 2)):
         e2e_step()
@@ -351,11 +410,52 @@ def run_ours(args, rank, local_rank, world):
     for _ in range(args.steps):
         e2e_step()
     barrier()
-    e2e_s = time.perf_counter() - t0
-    tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    e2e_value = world * B * args.steps / max_over_ranks(time.perf_counter() - t0)
+    e2e_parity = None
     if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / float(tt.item())
+        e2e_parity = float((out_host[rank * B:(rank + 1) * B].to(dev) - ll_d).abs().max().item())
+
+    # ---- strong scaling: BASELINE configs[2], a FIXED global batch cut across the ranks ----
+    strong = None
+    if world > 1 and not args.no_strong:
+        strong = []
+        for total in (4096, 32768):
+            A_dev = torch.as_tensor(go.synthetic_biggp_hypers(total, seed=7), device=dev)
+
+            def sharded():
+                return mfdist.log_likelihood_batch_sharded(gp, A_dev)
+
+            for _ in range(2):
+                got = sharded()
+            barrier()
+            e0, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                got = sharded()
+            e1_.record()
+            barrier()
+            ms_n = max_over_ranks(e0.elapsed_time(e1_)) / args.steps
+            # the same batch on ONE GPU of this box, same run: rank 0 alone, the others wait
+            ms_1, parity = 0.0, 0.0
+            if rank == 0:
+                alone = gp.log_likelihood_batch(A_dev)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(args.steps):
+                    alone = gp.log_likelihood_batch(A_dev)
+                e1_.record()
+                torch.cuda.synchronize()
+                ms_1 = e0.elapsed_time(e1_) / args.steps
+                ok = torch.isfinite(alone)
+                parity = float(((got[ok] - alone[ok]).abs() / alone[ok].abs()).max().item())
+                parity = parity if bool((torch.isfinite(got) == ok).all()) else float("inf")
+            barrier()
+            strong.append({"global_batch": total, "per_gpu_batch": total // world, "value": total / (ms_n * 1e-3),
+                           "unit": UNIT, "ms_per_step": ms_n, "single_gpu_ms_per_step": ms_1,
+                           "efficiency_vs_1gpu_same_run": ms_1 / (world * ms_n) if ms_n > 0 else None,
+                           "sharded_parity_max_rel": parity,
+                           "entry_point": "miniframe_b200.dist.log_likelihood_batch_sharded (device-resident batch)"})
+            del A_dev
 
     if rank != 0:
         if world > 1:
@@ -366,13 +466,15 @@ def run_ours(args, rank, local_rank, world):
     cpu = None
     parity = None
     if world == 1 and not args.no_cpu_baseline:
-        rate, done, vals, cores = cpu_port_evals(N, H, args.cpu_seconds, 512)
+        rate, done, vals, cores, kind = cpu_port_evals(N, H, args.cpu_seconds, 512)
         got = ll_d[:done].cpu().numpy()
         parity = float(np.max(np.abs(got - vals) / np.abs(vals)))
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "first %d of the %d hyper-parameter sets, oracle literal port of the "
-                         "reference (numpy %s + scipy LAPACK), pool of %d single-threaded workers"
-                         % (done, B, np.__version__, cores)}
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": "first %d of the %d hyper-parameter sets, %s (numpy %s + scipy LAPACK), pool of "
+                         "%d single-threaded workers"
+                         % (done, B, "the unmodified reference's BIGgp.log_likelihood (oracle/_ref)"
+                            if kind == "reference" else "oracle literal port of the reference",
+                            np.__version__, cores)}
 
     hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     try:
@@ -384,6 +486,9 @@ def run_ours(args, rank, local_rank, world):
     potrf_tflops = flops_per_eval(n) * per_launch / (potrf_ms * 1e-3) / 1e12
     build_gbs = build_bytes_per_eval(n) * per_launch / (build_ms * 1e-3) / 1e9
     fp64_peak = max(peaks.get("cublas_dgemm_4096_tflops", 0.0), peaks.get("dmma_probe_tflops", 0.0))
+    fp64_sustained = peaks.get("dmma_probe_sustained_tflops", 0.0)
+    potrf_traffic, potrf_note = ncu_traffic("mf_potrf_ll_kernel", n, per_launch)
+    build_traffic, build_note = ncu_traffic("mf_cov_build_big_il_kernel", n, per_launch)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -391,21 +496,25 @@ def run_ours(args, rank, local_rank, world):
         "config": config_dict(args, world),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT,
-                "h2d_bytes_per_step": int(H.nbytes + resid_bytes), "d2h_bytes_per_step": int(B * 8 * world)},
+                "h2d_bytes_per_step": int(H_global.nbytes), "d2h_bytes_per_step": int(B * 8 * world * world),
+                "entry_point": "BIGgp.log_likelihood_batch(host array)" if world == 1 else
+                               "dist.log_likelihood_batch_sharded(gp, host array of %d rows)" % (B * world),
+                "max_abs_diff_vs_device_timed_results": e2e_parity},
         "gpu_launches": gpu_launches,
         "roofline": {"kernel": "mf_potrf_ll_kernel", "bound": "tensor", "achieved": potrf_tflops,
                      "peak": fp64_peak, "unit": "TFLOP/s", "frac": potrf_tflops / fp64_peak,
-                     "traffic": NCU_POTRF_BYTES_PER_EVAL * per_launch / 1e9,
-                     "traffic_unit": "GB per launch (ncu dram read+write of a 296-matrix launch, "
-                                     "profiles/r1_summary.md, scaled to this launch)",
-                     "peak_source": "FP64 is not in MEASURED_PEAKS.json: max of cuBLAS DGEMM 4096^3 "
-                                    "(best of 5) and the DMMA register probe, both measured in this run",
+                     "peak_sustained": fp64_sustained,
+                     "frac_of_sustained": potrf_tflops / fp64_sustained if fp64_sustained else None,
+                     "traffic": potrf_traffic, "traffic_unit": potrf_note,
+                     "peak_source": "FP64 is not in MEASURED_PEAKS.json: `peak` = max of cuBLAS DGEMM 4096^3 "
+                                    "(best of 5) and the DMMA register probe in ~5 ms bursts, `peak_sustained` = "
+                                    "the same probe run for the duration of one factorisation launch; all "
+                                    "measured in this run",
                      "ms_per_launch": potrf_ms, "evals_per_launch": per_launch,
                      "flops_per_eval": flops_per_eval(n)},
-        "roofline_build": {"kernel": "mf_cov_build_kernel", "bound": "hbm", "achieved": build_gbs,
+        "roofline_build": {"kernel": "mf_cov_build_big_il_kernel", "bound": "hbm", "achieved": build_gbs,
                            "peak": hbm_peak, "unit": "GB/s", "frac": build_gbs / hbm_peak,
-                           "traffic": NCU_BUILD_BYTES_PER_EVAL * per_launch / 1e9,
-                           "traffic_unit": "GB per launch (ncu, scaled as above)",
+                           "traffic": build_traffic, "traffic_unit": build_note,
                            "peak_source": hbm_src, "ms_per_launch": build_ms,
                            "bytes_per_eval": build_bytes_per_eval(n)},
         "fp64_peaks_measured": peaks,
@@ -414,6 +523,8 @@ def run_ours(args, rank, local_rank, world):
         "non_pd_samples": n_fail,
         "kernel_share": {"build": build_ms / (build_ms + potrf_ms), "potrf": potrf_ms / (build_ms + potrf_ms)},
     }
+    if strong is not None:
+        line["strong"] = strong
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -431,6 +542,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=2,
                     help="likelihoods per host core per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling record (N > 1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -10,8 +10,10 @@
  *
  * Conventions
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
- *     its name ends in _host; the caller owns every buffer (the library
- *     allocates nothing after mf_create);
+ *     its name ends in _host; the caller owns every data buffer and the
+ *     workspace.  mf_create allocates the handle's own 1.2 MB of device scratch
+ *     (hand-out counter and group barriers of the factorisation); no call after
+ *     mf_create allocates, frees or synchronises;
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*;
  *     NULL = the default stream) and is asynchronous with respect to the host;
  *   - every function returns an mf_status (0 = ok), never throws;
@@ -41,7 +43,7 @@
 extern "C" {
 #endif
 
-#define MF_VERSION 100
+#define MF_VERSION 200
 
 typedef enum {
     MF_OK = 0,
@@ -94,12 +96,24 @@ typedef struct mf_handle_s* mf_handle_t;
 int  mf_version(void);
 const char* mf_status_string(int status);
 
-/* One handle per (device, caller thread).  Holds only device properties and
- * the last error text; no device memory. */
+/* One handle per (device, stream): it owns 1.2 MB of device scratch (the hand-out
+ * counter and the group barriers of mf_potrf_loglike), a small cache of TMA
+ * descriptors and the last error text, all of which concurrent launches would
+ * share.  Calls on one handle must therefore be issued to one stream at a time;
+ * different handles are independent (thread-safe across handles). */
 int  mf_create(mf_handle_t* out, int device);
 int  mf_destroy(mf_handle_t h);
 const char* mf_last_error(mf_handle_t h);
 int  mf_device_info(mf_handle_t h, int* sm_count, int* cc_major, int* cc_minor);
+
+/* Tuning / test knobs of one handle (0 restores the library's own choice):
+ *   "potrf_tile"   1: 64-row tiles, 2: 128-row tiles of the factorisation
+ *   "potrf_group"  1: one CTA per matrix, G > 1: G CTAs per matrix (cooperative)
+ *   "cov_ctas"     CTAs per sample of the covariance build
+ *   "experiment"   timing-experiment variants; rejected with MF_ERR_UNSUPPORTED
+ *                  unless the library was built with -DMF_EXPERIMENTS (the
+ *                  shipped library is not) */
+int  mf_set_option(mf_handle_t h, const char* name, int value);
 
 /* layout helpers (host arithmetic only) */
 int64_t mf_ld(int n);               /* leading dimension in doubles, multiple of 16 */
@@ -116,14 +130,33 @@ size_t  mf_workspace_bytes(int batch, int n);
  *   diag_add  [n]                   added to the diagonal (rverr^2 ... or yerr^2 or 1e-12)
  *   hyper     [batch x hyper_len]
  *   extra     [batch x extra_len]   or NULL when extra_len == 0
- *   full      0: lower triangle only (what the factorisation needs)
- *             1: the full symmetric square (what compute_matrix returns)
+ *   mode      MF_COV_LOWER: lower triangle only, the reference's row order
+ *               r = P * n_epochs + i (series P, epoch i);
+ *             MF_COV_FULL: the full symmetric square (what compute_matrix returns);
+ *             MF_COV_LOWER_INTERLEAVED: lower triangle in EPOCH-INTERLEAVED order
+ *               r = n_series * i + P, a symmetric permutation of K that leaves the
+ *               log-likelihood unchanged.  It turns the nine scattered output blocks
+ *               into one dense stream of 128-byte-aligned tiles written with TMA
+ *               stores, which is why mf_loglike uses it; BIGgp / BIGgpPlusJitt with
+ *               nugget == 0 only.  A residual used with such a matrix must be in the
+ *               same order (mf_interleave_resid).
  *   K         [batch] matrices, leading dimension ld, `stride` doubles apart
  */
+#define MF_COV_LOWER              0
+#define MF_COV_FULL               1
+#define MF_COV_LOWER_INTERLEAVED  2
 int mf_build_cov(mf_handle_t h, const mf_problem_t* prob, int batch,
                  const double* t, const double* diag_add,
-                 const double* hyper, const double* extra, int full,
+                 const double* hyper, const double* extra, int mode,
                  double* K, int64_t ld, int64_t stride, void* stream);
+
+/* dst[b][n_series * i + P] = src[b][P * n_epochs + i]: the residual y - mean
+ * (BIGgp.py:303) in the order of MF_COV_LOWER_INTERLEAVED.  src_stride may be 0
+ * (one residual for the whole batch); dst may be row n of the workspace matrices
+ * (dst_stride = mf_matrix_stride), from where mf_potrf_loglike takes it in place. */
+int mf_interleave_resid(mf_handle_t h, int batch, int n_series, int n_epochs,
+                        const double* src, int64_t src_stride,
+                        double* dst, int64_t dst_stride, void* stream);
 
 /*
  * Blocked left-looking Cholesky with the residual carried as row n, fused with
@@ -132,13 +165,15 @@ int mf_build_cov(mf_handle_t h, const mf_problem_t* prob, int batch,
  * SMALLgp.py:269-273).
  *   K      in: lower triangle of each matrix; out: L (lower) and, in row n, z = L^-1 r
  *   resid  [batch x n] with row stride resid_stride (0 = one residual shared by
- *          the whole batch), or NULL (z = 0, ll = -logdet - n/2 log 2pi)
+ *          the whole batch), or NULL (z = 0, ll = -logdet - n/2 log 2pi); may be
+ *          row n of the matrices themselves (resid = K + n * ld, resid_stride =
+ *          stride): it is then replaced by z in place
  *   ll     [batch] log-likelihood, -inf where info != 0
  *   info   [batch]
  * One CTA per matrix when batch >= 2 x SM count; with fewer matrices several CTAs
- * share each one (cooperative launch; the handle's scratch carries their
- * synchronisation words, so use one handle per stream).  The factor is the same,
- * bit for bit, either way.
+ * share each one (cooperative launch).  The handle's scratch carries the hand-out
+ * counter and the groups' synchronisation words: one handle per stream.  The
+ * factor is the same, bit for bit, either way.
  */
 int mf_potrf_loglike(mf_handle_t h, int batch, int n,
                      double* K, int64_t ld, int64_t stride,
@@ -150,6 +185,10 @@ int mf_potrf_loglike(mf_handle_t h, int batch, int n,
  * hyper-parameter set (BIGgp.py:281-312, BIGgpPlusJitt.py:285-318,
  * SMALLgp.py:252-277; the caller being examples/BIGgp_mcmc.py:47-64).
  * Processes the batch in chunks of floor(ws_bytes / matrix bytes) matrices.
+ * resid is given in the reference's order; for BIGgp / BIGgpPlusJitt the
+ * covariance is built and factorised in the epoch-interleaved order (the
+ * log-likelihood does not depend on it) and info[b] then counts pivots in that
+ * order.  The reference only ever tests info for zero (LinAlgError -> -inf).
  */
 int mf_loglike(mf_handle_t h, const mf_problem_t* prob, int batch,
                const double* t, const double* diag_add,

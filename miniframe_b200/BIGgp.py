@@ -291,11 +291,15 @@ class BIGgp(GPBase):
         Ks = S[:T, T:].contiguous()                       # (T, N)
         if extra_diag:
             Kss += extra_diag * torch.eye(T, dtype=torch.float64, device=Kss.device)
+        npar = _lib.KERNEL_NPAR[self._kernel_id()]
+        wn = float(hyper[0, npar - 1])
         if T == N:
             # square tstar: every kernel-class call adds wn^2 I (kernels.py:296)
-            npar = _lib.KERNEL_NPAR[self._kernel_id()]
-            wn = float(hyper[0, npar - 1])
             Ks += square_wn_coef * wn * wn * torch.eye(T, dtype=torch.float64, device=Ks.device)
+        elif min(T, N) == 1:
+            # one prediction time (or one observation): wn^2 diag(diag(ones_like(r))) is 1 x 1 and
+            # broadcasts, so every entry of K* gets the white noise (kernels.py:296-297)
+            Ks += square_wn_coef * wn * wn
         ld, stride = eng.ld(N), eng.matrix_stride(N)
         Kw = torch.zeros((1, stride // ld, ld), dtype=torch.float64, device=Ks.device)
         Kw[0, :N, :N] = S[T:, T:]

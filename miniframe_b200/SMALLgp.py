@@ -117,8 +117,8 @@ class SMALLgp(GPBase):
             ne = _lib.KERNEL_NPAR[prob.extra_kernel]
             if C is None or C.shape[1] < ne + M:
                 raise ValueError("need at least %d parameters per row in c" % (ne + M))
-            ccat = cat
-            if _is_torch(C) and not _is_torch(A):
+            ccat = np.concatenate           # by C's own array kind, whatever A is
+            if _is_torch(C):
                 import torch
                 ccat = torch.cat
             extra = ccat([C[:, :ne], C[:, C.shape[1] - M:]], 1)
@@ -216,9 +216,13 @@ class SMALLgp(GPBase):
         only_dd[0, npar:] = 0.0
         only_dd[0, npar + 3 * p + 1] = 1.0                       # a2 = 1: the block is ddK
         Ks += 4.0 * a1 * a3 * block(bare, only_dd, None)[:T, T:]
+        wn = float(hyper[0, npar - 1])
         if T == N:
-            wn = float(hyper[0, npar - 1])
             Ks += wn * wn * (a1 + a2 + a3) ** 2 * torch.eye(T, dtype=torch.float64, device=Ks.device)
+        elif min(T, N) == 1:
+            # one prediction time (or one observation): the reference's wn^2 diag(diag(ones_like(r)))
+            # is 1 x 1 and broadcasts over every entry of K* (kernels.py:296-297)
+            Ks += wn * wn * (a1 + a2 + a3) ** 2
         ld, stride = eng.ld(N), eng.matrix_stride(N)
         Kw = torch.zeros((1, stride // ld, ld), dtype=torch.float64, device=Ks.device)
         Kw[0, :N, :N] = Kn

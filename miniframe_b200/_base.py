@@ -81,10 +81,20 @@ class GPBase(object):
         return _lib.KERNEL_IDS[name]
 
     def _dev(self, key, make):
+        """Device copy of the host array ``make()``.  The reference rereads t, y and the errors on
+        every call, so the copy is refreshed whenever the host values differ from the ones it was
+        made from (reassigned or edited in place); comparing a few thousand doubles costs
+        microseconds, an upload would cost a launch.  Non-finite data raise ValueError here, as
+        scipy's check_finite does inside the reference's cho_factor / cho_solve (BIGgp.py:306-307)."""
         cache = self.__dict__.setdefault("_device_cache", {})
-        if key not in cache:
-            cache[key] = self.engine.tensor(make())
-        return cache[key]
+        host = np.ascontiguousarray(make(), dtype=float)
+        hit = cache.get(key)
+        dev_index = self.engine.device.index
+        if hit is None or hit[2] != dev_index or hit[0].shape != host.shape or not np.array_equal(hit[0], host):
+            self._check_finite(host)
+            hit = (host.copy(), self.engine.tensor(host), dev_index)
+            cache[key] = hit
+        return hit[1]
 
     def _y_flat(self):
         raise NotImplementedError

@@ -1,5 +1,7 @@
 """Device engine: torch tensors hold every buffer, ctypes calls the sm_100a
-kernels.  One engine per process (one process per GPU)."""
+kernels.  One engine per process (one process per GPU); inside it one library
+handle per CUDA stream (a handle's scratch - the hand-out counter and group
+barriers of the factorisation - must not be shared by concurrent launches)."""
 import ctypes
 
 import numpy as np
@@ -30,18 +32,42 @@ class Engine(object):
         if device is None:
             device = torch.cuda.current_device()
         self.device = torch.device("cuda", device)
-        self.handle = ctypes.c_void_p()
-        st = self.lib.mf_create(ctypes.byref(self.handle), self.device.index)
-        if st != _lib.MF_OK:
-            raise _lib.MiniframeError("mf_create(device=%d) failed: %s" % (
-                self.device.index, self.lib.mf_status_string(st).decode()))
-        self._ws = None
+        self._handles = {}                  # cuda_stream -> mf_handle_t
+        self._options = {}
+        self._ws = {}                       # cuda_stream -> workspace buffer
         self.max_workspace_bytes = None     # None -> 70 % of the free device memory
         self.launches = 0                   # kernels this engine launched (bench bookkeeping)
+        self.handle                         # fail now if the device is not a B200
 
     # -- helpers -----------------------------------------------------------
+    def _stream_id(self):
+        return int(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def handle(self):
+        """The library handle of torch's current stream (created on first use)."""
+        sid = self._stream_id()
+        h = self._handles.get(sid)
+        if h is None:
+            h = ctypes.c_void_p()
+            st = self.lib.mf_create(ctypes.byref(h), self.device.index)
+            if st != _lib.MF_OK:
+                raise _lib.MiniframeError("mf_create(device=%d) failed: %s" % (
+                    self.device.index, self.lib.mf_status_string(st).decode()))
+            for name, value in self._options.items():
+                self.lib.mf_set_option(h, name.encode(), int(value))
+            self._handles[sid] = h
+        return h
+
+    def set_option(self, name, value):
+        """mf_set_option on every handle of this engine (see include/miniframe_b200.h)."""
+        self._options[name] = int(value)
+        for h in self._handles.values():
+            st = self.lib.mf_set_option(h, name.encode(), int(value))
+            _lib.check(self.lib, h, st, "mf_set_option(%s)" % name)
+
     def stream(self):
-        return ctypes.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+        return ctypes.c_void_p(self._stream_id())
 
     def tensor(self, x, dtype=None):
         torch = _torch()
@@ -64,31 +90,40 @@ class Engine(object):
         """A cached byte buffer holding as many of `batch` matrices as memory allows."""
         torch = _torch()
         per = self.matrix_stride(n) * 8
-        if (self._ws is not None and self._ws.numel() >= batch * per and
+        sid = self._stream_id()
+        ws = self._ws.get(sid)
+        if (ws is not None and ws.numel() >= batch * per and
                 (self.max_workspace_bytes is None or batch * per <= self.max_workspace_bytes)):
-            return self._ws, batch * per          # the cached buffer already holds the whole batch
+            return ws, batch * per                # the cached buffer already holds the whole batch
         cap = self.max_workspace_bytes
         if cap is None:
             free, _ = torch.cuda.mem_get_info(self.device)
-            have = 0 if self._ws is None else self._ws.numel()
+            have = 0 if ws is None else ws.numel()
             cap = int(0.7 * (free + have))
         count = max(1, min(batch, cap // per))
         need = count * per
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = None
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        return self._ws, need
+        if ws is None or ws.numel() < need:
+            self._ws.pop(sid, None)
+            ws = None
+            ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._ws[sid] = ws
+        return ws, need
+
+    def drop_workspaces(self):
+        self._ws.clear()
 
     # -- kernels -----------------------------------------------------------
-    def build_cov(self, prob, t, diag_add, hyper, extra, full=True):
-        """Returns the (B, rows, ld) workspace tensor (rows = stride / ld >= n + 1); [:, :n, :n] is K."""
+    def build_cov(self, prob, t, diag_add, hyper, extra, full=True, interleaved=False):
+        """Returns the (B, rows, ld) workspace tensor (rows = stride / ld >= n + 1); [:, :n, :n] is K
+        (``interleaved``: lower triangle in the epoch-interleaved order r = n_series * i + P)."""
         torch = _torch()
         B = hyper.shape[0]
         n = prob.n_series * prob.n_epochs
         ld, stride = self.ld(n), self.matrix_stride(n)
         K = torch.zeros((B, stride // ld, ld), dtype=torch.float64, device=self.device)
         st = self.lib.mf_build_cov(self.handle, ctypes.byref(prob), B, self.ptr(t), self.ptr(diag_add),
-                                   self.ptr(hyper), self.ptr(extra), 1 if full else 0,
+                                   self.ptr(hyper), self.ptr(extra),
+                                   _lib.COV_LOWER_INTERLEAVED if interleaved else (_lib.COV_FULL if full else _lib.COV_LOWER),
                                    self.ptr(K), ld, stride, self.stream())
         _lib.check(self.lib, self.handle, st, "mf_build_cov")
         self.launches += 1
@@ -136,7 +171,8 @@ class Engine(object):
                                  self.ptr(ws), ws_bytes, self.ptr(ll), self.ptr(info), self.stream())
         _lib.check(self.lib, self.handle, st, "mf_loglike")
         per = self.matrix_stride(n) * 8
-        self.launches += 2 * (-(-B // max(1, ws_bytes // per)))
+        interleaved = prob.framework != _lib.FRAMEWORK_SMALLGP and prob.nugget == 0.0 and resid is not None
+        self.launches += (3 if interleaved else 2) * (-(-B // max(1, ws_bytes // per)))
         return ll, info
 
     def probe_fp64(self, mode, iters=20000):

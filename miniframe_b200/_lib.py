@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libminiframe_b200.so")
 
 MF_OK = 0
+COV_LOWER, COV_FULL, COV_LOWER_INTERLEAVED = 0, 1, 2
 FRAMEWORK_BIGGP, FRAMEWORK_BIGGP_JITT, FRAMEWORK_SMALLGP = 0, 1, 2
 KERNEL_NONE, KERNEL_SE, KERNEL_QP = -1, 0, 1
 KERNEL_IDS = {"SquaredExponential": KERNEL_SE, "QuasiPeriodic": KERNEL_QP}
@@ -34,11 +35,14 @@ SIGNATURES = {
     "mf_destroy": (c_int, [c_void_p]),
     "mf_last_error": (c_char_p, [c_void_p]),
     "mf_device_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "mf_set_option": (c_int, [c_void_p, c_char_p, c_int]),
     "mf_ld": (c_int64, [c_int]),
     "mf_matrix_stride": (c_int64, [c_int]),
     "mf_workspace_bytes": (c_size_t, [c_int, c_int]),
     "mf_build_cov": (c_int, [c_void_p, POINTER(Problem), c_int, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p]),
+    "mf_interleave_resid": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int64, c_void_p,
+                                    c_int64, c_void_p]),
     "mf_potrf_loglike": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, c_int64, c_void_p,
                                  c_int64, c_void_p, c_void_p, c_void_p]),
     "mf_loglike": (c_int, [c_void_p, POINTER(Problem), c_int, c_void_p, c_void_p, c_void_p,

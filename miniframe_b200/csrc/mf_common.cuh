@@ -1,5 +1,6 @@
 // Shared host/device helpers for the sm_100a kernels of miniframe_b200.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -7,18 +8,56 @@
 
 #include "../../include/miniframe_b200.h"
 
+// Tensor maps (TMA descriptors) are encoded on the host; a handle keeps the last few, keyed by
+// everything that goes into the encoding, so a sampler that calls with the same workspace
+// thousands of times encodes once.
+struct mf_tmap_key {
+    int kind;                 // 1: factorisation ring (5-D load), 2: covariance tiles (3-D store)
+    const void* base;
+    int64_t ld, stride;
+    int n, batch;
+};
+struct mf_tmap_slot {
+    mf_tmap_key key;
+    alignas(64) CUtensorMap map;
+};
+constexpr int MF_TMAP_SLOTS = 8;
+
+// options a caller (the tests, the tuning scripts) may set through mf_set_option
+struct mf_options {
+    int potrf_tile;           // 0 = choose, 1 = 64-row tiles, 2 = 128-row tiles
+    int potrf_group;          // 0 = choose, 1 = one CTA per matrix, G > 1 = G CTAs per matrix
+    int cov_ctas;             // 0 = choose, else CTAs per sample of the covariance build
+    int experiment;           // timing-experiment variant (only with -DMF_EXPERIMENTS builds)
+};
+
 struct mf_handle_s {
     int device;
     int sm_count;
     int cc_major, cc_minor;
     size_t smem_optin;
-    // scratch of the cooperative (several CTAs per matrix) factorisation, allocated once by
-    // mf_create: per group 8 synchronisation words and the 8 negated 8x8 inverses (512 doubles)
+    // Device scratch owned by the handle, allocated once by mf_create (1.2 MB): the hand-out
+    // counter of the persistent factorisation and, for its cooperative variant (several CTAs per
+    // matrix), per group 8 synchronisation words and the 8 negated 8x8 inverses (512 doubles).
+    // Launches on one handle share it: one handle per stream.
     unsigned* coop_sync;
     double* coop_dinv;
     int coop_groups;
+    mf_options opt;
+    mf_tmap_slot tmaps[MF_TMAP_SLOTS];
+    int tmap_next;
     char err[512];
 };
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point query (no link-time libcuda)
+typedef CUresult (*mf_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                      CUtensorMapFloatOOBfill);
+mf_tmap_encode_fn mf_tmap_encoder(mf_handle_s* h);
+// cached lookup: returns the slot holding `key`'s map, or nullptr with *fresh pointing at the slot
+// the caller must encode into
+const CUtensorMap* mf_tmap_find(mf_handle_s* h, const mf_tmap_key& key, mf_tmap_slot** fresh);
 
 #define MF_CUDA_CHECK(h, call)                                                        \
     do {                                                                              \

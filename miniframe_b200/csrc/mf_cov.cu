@@ -268,6 +268,170 @@ mf_cov_build_big_lower_kernel(const CovParams p) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------
+// Rajpaul likelihood path in EPOCH-INTERLEAVED order (mode MF_COV_LOWER_INTERLEAVED): row and
+// column r = 3 i + P instead of P N + i, a symmetric permutation of K that leaves the
+// log-likelihood unchanged (the residual is permuted with it, mf_interleave_resid).  The nine
+// values a pair of epochs (i > j) feeds - six blocks at lag t_i - t_j, three at t_j - t_i - then
+// form one 3 x 3 micro-block, a 32 x 32 pair tile is a dense 96 x 96 tile of the matrix, and the
+// nine output streams of the standard order (block offsets N * 8 bytes, not line-aligned, six
+// megabytes apart) become ONE stream of 768-byte, 128-byte-aligned row segments.  Half a pair tile
+// (16 x 32 pairs = 48 x 96 doubles) is staged in shared memory and written by a TMA bulk-tensor
+// store (SASS UTMASTG) that overlaps the arithmetic of the next half; tiles on the diagonal are
+// written row by row so that only the lower triangle is touched (algorithmic bytes = bytes
+// written).  Same per-entry arithmetic as the standard-order kernels: the matrices are equal bit
+// for bit up to the permutation.  The coefficient table of a sample is computed by 26 threads
+// in parallel, one field each (a single thread needs ~3.6 us for its six divisions in sequence).
+// ---------------------------------------------------------------------------------
+constexpr int IL_TI = 16;                    // epochs i per half tile
+constexpr int IL_ROWS = 3 * IL_TI;           // 48 matrix rows
+constexpr int IL_COLS = 3 * TT;              // 96 matrix columns
+constexpr int IL_BUF = IL_ROWS * IL_COLS;    // doubles per staging buffer (36,864 bytes)
+
+struct CovILParams {
+    alignas(64) CUtensorMap tmap;            // {column, row, matrix} over the chunk, box 96 x 48 x 1
+    CovParams c;
+};
+
+__device__ __forceinline__ void tma_store_tile(const CUtensorMap* tm, uint32_t src, int c0, int r0, int mat) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 ::"l"(tm), "r"(c0), "r"(r0), "r"(mat), "r"(src)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+template <int KERNEL>
+__global__ void __launch_bounds__(THREADS, 3)
+mf_cov_build_big_il_kernel(const __grid_constant__ CovILParams q) {
+    const CovParams& p = q.c;
+    extern __shared__ __align__(128) unsigned char il_smem_raw[];
+    // the source of a bulk-tensor store must be 128-byte aligned: align by hand (128 spare bytes)
+    unsigned char* const il_smem = il_smem_raw + ((128u - (smem_u32(il_smem_raw) & 127u)) & 127u);
+    double* const stage = reinterpret_cast<double*>(il_smem);                    // 2 x [48][96]
+    BigCoefs& sc = *reinterpret_cast<BigCoefs*>(il_smem + 2 * IL_BUF * sizeof(double));
+
+    const int N = p.prob.n_epochs;
+    const int n = 3 * N;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t ld = p.ld;
+    const int npar = KERNEL == MF_KERNEL_QP ? 4 : 2;
+    const bool jitt = p.prob.framework == MF_FRAMEWORK_BIGGP_JITT && p.extra != nullptr;
+    unsigned half_count = 0;                 // halves this CTA has staged: buffer = half_count & 1
+
+    for (int b = blockIdx.y; b < p.batch; b += gridDim.y) {
+        __syncthreads();                     // the previous sample's readers are done with sc
+        {
+            const double* hy = p.hyper + (size_t)b * p.prob.hyper_len;
+            if (tid < MF_KC_FIELDS) {
+                reinterpret_cast<double*>(&sc.k)[tid] = mf_kc_field(KERNEL, hy, tid);
+                reinterpret_cast<double*>(&sc.e)[tid] = 0.0;
+            } else if (tid >= 16 && tid < 22) {
+                int P, Q;
+                mf_big_pair_index(tid - 16, P, Q);
+                const BlockCoef u = mf_big_pair_coef(tid - 16, hy + npar);
+                mf_set_pair(sc, P, Q, u.cE, u.cAE, u.cGdd, u.cH, u.cG4, u.cW);
+            } else if (tid >= 24 && tid < 27) {
+                const int k = tid - 24;
+                sc.amp2[k] = 0.0;
+                sc.jit2[k] = jitt ? dm(p.extra[(size_t)b * p.prob.extra_len + k], p.extra[(size_t)b * p.prob.extra_len + k]) : 0.0;
+            }
+        }
+        __syncthreads();
+        const double e00 = sc.c[0][0].cE, g00 = sc.c[0][0].cGdd;
+        const double e11 = sc.c[1][1].cE;
+        const double e22 = sc.c[2][2].cE, g22 = sc.c[2][2].cGdd;
+        const double e10 = sc.c[1][0].cE, a10 = sc.c[1][0].cAE;
+        const double e20 = sc.c[2][0].cE, g20 = sc.c[2][0].cGdd, a20 = sc.c[2][0].cAE;
+        const double e21 = sc.c[2][1].cE, a21 = sc.c[2][1].cAE;
+        double* const Kb = p.K + (size_t)b * p.stride;
+
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            int tile_i = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
+            while ((tile_i + 1) * (tile_i + 2) / 2 <= tile) ++tile_i;
+            while (tile_i * (tile_i + 1) / 2 > tile) --tile_i;
+            const int tile_j = tile - tile_i * (tile_i + 1) / 2;
+            const int j0 = tile_j * TT;
+            const bool diag_tile = tile_i == tile_j;
+            const int j = j0 + lane;
+            const double tj = (j < N) ? p.t[j] : 0.0;
+
+            for (int half = 0; half < 2; ++half) {
+                const int i0 = tile_i * TT + half * IL_TI;
+                if (i0 >= N) break;
+                double* const buf = stage + (half_count & 1u) * IL_BUF;
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int il = warp + 8 * rr;
+                    const int i = i0 + il;
+                    if (i >= N || j >= N || (diag_tile && i < j)) continue;
+                    Bases bs;
+                    mf_bases<KERNEL, false>(p.t[i] - tj, sc.k, bs);
+                    double* m = buf + (3 * il) * IL_COLS + 3 * lane;      // micro-block (3 i + P, 3 j + Q)
+                    if (i != j) {
+                        const double u10 = dm(e10, bs.E);
+                        const double u20 = df(g20, bs.Gdd, dm(e20, bs.E));
+                        const double u21 = dm(e21, bs.E);
+                        m[0] = df(g00, bs.Gdd, dm(e00, bs.E));
+                        m[1] = df(a10, -bs.AE, u10);                      // (0,1) = block (1,0) at lag -r
+                        m[2] = df(a20, -bs.AE, u20);
+                        m[IL_COLS] = df(a10, bs.AE, u10);
+                        m[IL_COLS + 1] = dm(e11, bs.E);
+                        m[IL_COLS + 2] = df(a21, -bs.AE, u21);
+                        m[2 * IL_COLS] = df(a20, bs.AE, u20);
+                        m[2 * IL_COLS + 1] = df(a21, bs.AE, u21);
+                        m[2 * IL_COLS + 2] = df(g22, bs.Gdd, dm(e22, bs.E));
+                    } else {
+                        // same epoch: white noise on every block, errors and jitter on the diagonal
+                        for (int P = 0; P < 3; ++P)
+                            for (int Q = 0; Q <= P; ++Q)
+                                m[P * IL_COLS + Q] = mf_entry(sc, bs, P, Q, true, 0.0, p.diag_add[P * N + i], 0.0);
+                    }
+                }
+                // staged values -> async proxy; the store of the previous half (other buffer) must
+                // have read its buffer before anyone refills it after the next barrier
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncthreads();
+                if (!diag_tile) {
+                    if (tid == 0) tma_store_tile(&q.tmap, smem_u32(buf), 3 * j0, 3 * i0, b);
+                } else {
+                    // rows of the lower triangle only: row R holds columns 3 j0 .. R
+#pragma unroll 1
+                    for (int rl = warp; rl < IL_ROWS; rl += THREADS / 32) {
+                        const int R = 3 * i0 + rl;
+                        if (R >= n) break;
+                        const int ncols = R - 3 * j0 + 1;
+                        const double* src = buf + rl * IL_COLS;
+                        double* dst = Kb + (size_t)R * ld + 3 * j0;
+                        for (int c = 2 * lane; c < ncols; c += 64) {
+                            if (c + 1 < ncols)
+                                *reinterpret_cast<double2*>(dst + c) = *reinterpret_cast<const double2*>(src + c);
+                            else
+                                dst[c] = src[c];
+                        }
+                    }
+                }
+                ++half_count;
+            }
+        }
+    }
+    // the last store still reads shared memory: it must have completed before the CTA retires
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// residual rows into the same order: dst[M i + P] = src[P N + i]
+__global__ void mf_interleave_resid_kernel(int batch, int M, int N, const double* src, int64_t src_stride,
+                                           double* dst, int64_t dst_stride) {
+    const int n = M * N;
+    for (int b = blockIdx.y; b < batch; b += gridDim.y) {
+        const double* s = src + (size_t)b * src_stride;
+        double* d = dst + (size_t)b * dst_stride;
+        for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x)
+            d[r] = s[(r % M) * N + r / M];
+    }
+}
+
 }  // namespace
 
 // CTAs per sample (grid.x; the samples are grid.y, so the CTAs of one sample are scheduled
@@ -277,6 +441,7 @@ mf_cov_build_big_lower_kernel(const CovParams p) {
 // keeping only ~32 matrices in flight makes the same stores 17 % faster (measured: 1 CTA per
 // sample 3.99 TB/s, 34-46 CTAs 4.69 TB/s, 136 CTAs - one tile each - 4.04 TB/s).
 static int cov_ctas_per_sample(mf_handle_t h, int samples, int n_tiles) {
+    if (h->opt.cov_ctas > 0) return h->opt.cov_ctas < n_tiles ? h->opt.cov_ctas : n_tiles;
     const int resident = 8 * h->sm_count;
     int bx = (resident + samples - 1) / samples;
     const int spread = (resident + 31) / 32;
@@ -300,12 +465,64 @@ static int launch_cov(mf_handle_t h, const CovParams& p, cudaStream_t st) {
     return MF_OK;
 }
 
+// interleaved order, BIGgp family: TMA-stored dense tiles
+template <int KERNEL>
+static int launch_cov_il(mf_handle_t h, const CovParams& p, cudaStream_t st) {
+    CovILParams q;
+    q.c = p;
+    const int n = 3 * p.prob.n_epochs;
+    mf_tmap_key key = {2, p.K, p.ld, p.stride, n, p.batch};
+    mf_tmap_slot* slot = nullptr;
+    const CUtensorMap* tm = mf_tmap_find(h, key, &slot);
+    if (!tm) {
+        mf_tmap_encode_fn encode = mf_tmap_encoder(h);
+        if (!encode) return MF_ERR_CUDA;
+        const cuuint64_t gdim[3] = {(cuuint64_t)n, (cuuint64_t)n, (cuuint64_t)p.batch};
+        const cuuint64_t gstr[2] = {(cuuint64_t)(p.ld * 8), (cuuint64_t)(p.stride * 8)};
+        const cuuint32_t box[3] = {IL_COLS, IL_ROWS, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult cr = encode(&slot->map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, p.K, gdim, gstr, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) MF_FAIL(h, MF_ERR_CUDA, "cuTensorMapEncodeTiled (covariance tiles) failed with %d", (int)cr);
+        slot->key.kind = key.kind;
+        tm = &slot->map;
+    }
+    q.tmap = *tm;
+    const size_t smem = 2 * IL_BUF * sizeof(double) + sizeof(BigCoefs) + 128;
+    MF_CUDA_CHECK(h, cudaFuncSetAttribute(mf_cov_build_big_il_kernel<KERNEL>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int by = p.batch < 65535 ? p.batch : 65535;
+    const int bx = cov_ctas_per_sample(h, by, p.n_tiles);
+    mf_cov_build_big_il_kernel<KERNEL><<<dim3(bx, by), THREADS, smem, st>>>(q);
+    MF_CUDA_CHECK(h, cudaGetLastError());
+    return MF_OK;
+}
+
+extern "C" int mf_interleave_resid(mf_handle_t h, int batch, int n_series, int n_epochs,
+                                   const double* src, int64_t src_stride, double* dst,
+                                   int64_t dst_stride, void* stream) {
+    if (!h) return MF_ERR_INVALID;
+    if (!src || !dst) MF_FAIL(h, MF_ERR_INVALID, "null pointer");
+    if (batch <= 0 || n_series < 1 || n_series > MF_MAX_SERIES || n_epochs < 1)
+        MF_FAIL(h, MF_ERR_INVALID, "bad batch/n_series/n_epochs");
+    const int n = n_series * n_epochs;
+    const int bx = (n + 255) / 256 < 64 ? (n + 255) / 256 : 64;
+    mf_interleave_resid_kernel<<<dim3(bx, batch < 65535 ? batch : 65535), 256, 0, (cudaStream_t)stream>>>(
+        batch, n_series, n_epochs, src, src_stride, dst, dst_stride);
+    MF_CUDA_CHECK(h, cudaGetLastError());
+    return MF_OK;
+}
+
 extern "C" int mf_build_cov(mf_handle_t h, const mf_problem_t* prob, int batch, const double* t,
                             const double* diag_add, const double* hyper, const double* extra,
-                            int full, double* K, int64_t ld, int64_t stride, void* stream) {
+                            int mode, double* K, int64_t ld, int64_t stride, void* stream) {
     if (!h) return MF_ERR_INVALID;
     if (!prob || !t || !diag_add || !hyper || !K) MF_FAIL(h, MF_ERR_INVALID, "null pointer");
     if (batch <= 0) MF_FAIL(h, MF_ERR_INVALID, "batch must be positive");
+    if (mode != MF_COV_LOWER && mode != MF_COV_FULL && mode != MF_COV_LOWER_INTERLEAVED)
+        MF_FAIL(h, MF_ERR_INVALID, "unknown covariance mode %d", mode);
+    const int full = mode == MF_COV_FULL;
     const int M = prob->n_series, N = prob->n_epochs;
     if (M < 1 || M > MF_MAX_SERIES || N < 1) MF_FAIL(h, MF_ERR_INVALID, "bad n_series/n_epochs");
     if (prob->kernel != MF_KERNEL_SE && prob->kernel != MF_KERNEL_QP)
@@ -345,6 +562,14 @@ extern "C" int mf_build_cov(mf_handle_t h, const mf_problem_t* prob, int batch, 
     p.stride = stride;
     cudaStream_t st = (cudaStream_t)stream;
     const bool high = prob->framework == MF_FRAMEWORK_SMALLGP;
+    if (mode == MF_COV_LOWER_INTERLEAVED) {
+        if (high || prob->nugget != 0.0)
+            MF_FAIL(h, MF_ERR_UNSUPPORTED, "the interleaved order is built for BIGgp / BIGgpPlusJitt without nugget");
+        if (((uintptr_t)K & 15) != 0 || (ld & 1) != 0 || (stride & 1) != 0)
+            MF_FAIL(h, MF_ERR_INVALID, "K must be 16-byte aligned, ld and stride even");
+        return prob->kernel == MF_KERNEL_QP ? launch_cov_il<MF_KERNEL_QP>(h, p, st)
+                                             : launch_cov_il<MF_KERNEL_SE>(h, p, st);
+    }
     if (!high && !p.full && prob->nugget == 0.0) {
         const int by = batch < 65535 ? batch : 65535;
         const int bx = cov_ctas_per_sample(h, by, p.n_tiles);

@@ -37,6 +37,15 @@ struct SampleCoefs {
     BlockCoef c[MF_MAX_SERIES][MF_MAX_SERIES];   // [row block][col block]
 };
 
+// the three-series (BIGgp / BIGgpPlusJitt) subset of SampleCoefs, same member names
+struct BigCoefs {
+    KernConst k;
+    KernConst e;                 // unused (amp2 == 0)
+    double amp2[3];
+    double jit2[3];
+    BlockCoef c[3][3];
+};
+
 // E, Gdd, G4 are even in the lag and AE is odd.  H is odd for the SE family but NOT
 // for the quasi-periodic one: the reference builds it from sin*sin (quirk Q4,
 // kernels.py:449), so H(-r) != -H(r) and both are kept: Hf = H(r), Hr = H(-r).
@@ -44,39 +53,53 @@ struct Bases {
     double E, AE, Gdd, Hf, Hr, G4;
 };
 
-__device__ inline void mf_kern_const(int kernel, const double* p, KernConst& o) {
-    if (kernel == MF_KERNEL_QP) {      // (ell_e, ell_p, period, wn), kernels.py:282
-        double le = p[0], lp = p[1], P = p[2], wn = p[3];
-        double f2 = lp * lp, f3 = le * le;
-        o.P = P;
-        o.wn2 = wn * wn;
-        o.i_f2 = 1.0 / f2;
-        o.i_f3 = 1.0 / f3;
-        o.i_f2P = 1.0 / (f2 * P);
-        o.i_f2P2 = 1.0 / (f2 * (P * P));
-        o.i_f2P3 = 1.0 / (f2 * (P * P * P));
-        o.i_f2P4 = 1.0 / (f2 * ((P * P) * (P * P)));
-        o.i_l4 = o.i_l6 = o.i_l8 = 0.0;
-    } else {                           // (ell, wn), kernels.py:91
-        double l = p[0], wn = p[1];
-        double f2 = l * l;
-        o.P = 1.0;
-        o.wn2 = wn * wn;
-        o.i_f2 = 1.0 / f2;
-        o.i_f3 = 0.0;
-        o.i_f2P = o.i_f2P2 = o.i_f2P3 = o.i_f2P4 = 0.0;
-        o.i_l4 = 1.0 / (f2 * f2);
-        o.i_l6 = 1.0 / (f2 * f2 * f2);
-        o.i_l8 = 1.0 / ((f2 * f2) * (f2 * f2));
-    }
-}
-
 // Explicitly rounded FP64 operations: the compiler neither fuses nor splits these,
 // so every inlined instance of the covariance algebra performs the same IEEE
 // operations and K(i, j) == K(j, i) bit for bit whichever thread/slot computed it.
 __device__ __forceinline__ double dm(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double da(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double df(double a, double b, double c) { return __fma_rn(a, b, c); }
+
+constexpr int MF_KC_FIELDS = 11;
+static_assert(sizeof(KernConst) == MF_KC_FIELDS * sizeof(double), "KernConst is an array of doubles");
+
+// Field `f` of the per-sample kernel constants (the order of the struct's members).  One
+// function for the serial set-up (all fields by one thread) and the parallel one (a field per
+// thread), every operation explicitly rounded: both give the same bits.
+__device__ __forceinline__ double mf_kc_field(int kernel, const double* p, int f) {
+    if (kernel == MF_KERNEL_QP) {      // (ell_e, ell_p, period, wn), kernels.py:282
+        const double le = p[0], lp = p[1], P = p[2], wn = p[3];
+        const double f2 = dm(lp, lp), f3 = dm(le, le), P2 = dm(P, P);
+        switch (f) {
+            case 0: return P;
+            case 1: return dm(wn, wn);
+            case 2: return __ddiv_rn(1.0, f2);
+            case 3: return __ddiv_rn(1.0, f3);
+            case 4: return __ddiv_rn(1.0, dm(f2, P));
+            case 5: return __ddiv_rn(1.0, dm(f2, P2));
+            case 6: return __ddiv_rn(1.0, dm(f2, dm(P2, P)));
+            case 7: return __ddiv_rn(1.0, dm(f2, dm(P2, P2)));
+            default: return 0.0;
+        }
+    }
+    const double l = p[0], wn = p[1];  // (ell, wn), kernels.py:91
+    const double f2 = dm(l, l), f4 = dm(f2, f2);
+    switch (f) {
+        case 0: return 1.0;
+        case 1: return dm(wn, wn);
+        case 2: return __ddiv_rn(1.0, f2);
+        case 8: return __ddiv_rn(1.0, f4);
+        case 9: return __ddiv_rn(1.0, dm(f4, f2));
+        case 10: return __ddiv_rn(1.0, dm(f4, f4));
+        default: return 0.0;
+    }
+}
+
+__device__ inline void mf_kern_const(int kernel, const double* p, KernConst& o) {
+    double* out = reinterpret_cast<double*>(&o);
+#pragma unroll
+    for (int f = 0; f < MF_KC_FIELDS; ++f) out[f] = mf_kc_field(kernel, p, f);
+}
 
 #define MF_4PI   (4.0 * MF_PI)
 #define MF_4PI2  (4.0 * MF_PI * MF_PI)
@@ -165,7 +188,8 @@ __device__ __forceinline__ double mf_kernel_value(int kernel, double r_signed, c
     return exp(dm(dm(-0.5, dm(r, r)), k.i_f2));
 }
 
-__device__ inline void mf_set_pair(SampleCoefs& sc, int p, int q, double cE, double cAE,
+template <typename SC>
+__device__ inline void mf_set_pair(SC& sc, int p, int q, double cE, double cAE,
                                    double cGdd, double cH, double cG4, double cW) {
     BlockCoef u = {cE, cAE, cGdd, cH, cG4, cW};
     sc.c[p][q] = u;
@@ -173,6 +197,30 @@ __device__ inline void mf_set_pair(SampleCoefs& sc, int p, int q, double cE, dou
         BlockCoef l = {cE, -cAE, cGdd, cH, cG4, cW};
         sc.c[q][p] = l;
     }
+}
+
+// BIGgp.py:167-234, block order [rv, rhk, bis]: coefficients of the upper-form pair `idx`
+// (0: (0,0), 1: (1,1), 2: (2,2), 3: (0,1), 4: (0,2), 5: (1,2)) from the scaling parameters.
+// Explicitly rounded, shared by the serial and the parallel set-up.
+__device__ __forceinline__ BlockCoef mf_big_pair_coef(int idx, const double* s5) {
+    const double vc = s5[0], vr = s5[1], lc = s5[2], bc = s5[3], br = s5[4];
+    BlockCoef u = {0, 0, 0, 0, 0, 0};
+    switch (idx) {
+        case 0: u.cE = dm(vc, vc); u.cGdd = dm(vr, vr); u.cW = dm(da(vc, vr), da(vc, vr)); break;
+        case 1: u.cE = dm(lc, lc); u.cW = dm(lc, lc); break;
+        case 2: u.cE = dm(bc, bc); u.cGdd = dm(br, br); u.cW = dm(da(bc, br), da(bc, br)); break;
+        case 3: u.cE = dm(vc, lc); u.cAE = -dm(vr, lc); u.cW = da(dm(vc, lc), dm(vr, lc)); break;
+        case 4:
+            u.cE = dm(vc, bc); u.cAE = da(dm(vc, br), -dm(vr, bc)); u.cGdd = dm(vr, br);
+            u.cW = da(da(da(dm(vc, bc), dm(vr, br)), dm(vc, br)), dm(vr, bc));
+            break;
+        default: u.cE = dm(lc, bc); u.cAE = dm(lc, br); u.cW = da(dm(lc, bc), dm(lc, br)); break;
+    }
+    return u;
+}
+__device__ __forceinline__ void mf_big_pair_index(int idx, int& p, int& q) {
+    p = idx < 3 ? idx : (idx == 5 ? 1 : 0);
+    q = idx < 3 ? idx : (idx == 3 ? 1 : 2);
 }
 
 // Per-sample coefficient table from the raw hyper-parameter rows.
@@ -215,24 +263,21 @@ __device__ inline void mf_make_coefs(const mf_problem_t& pb, const double* hyper
             }
         }
     } else {
-        // BIGgp.py:167-234; block order [rv, rhk, bis]
-        const double vc = hyper[npar], vr = hyper[npar + 1], lc = hyper[npar + 2],
-                     bc = hyper[npar + 3], br = hyper[npar + 4];
-        mf_set_pair(sc, 0, 0, vc * vc, 0, vr * vr, 0, 0, (vc + vr) * (vc + vr));
-        mf_set_pair(sc, 1, 1, lc * lc, 0, 0, 0, 0, lc * lc);
-        mf_set_pair(sc, 2, 2, bc * bc, 0, br * br, 0, 0, (bc + br) * (bc + br));
-        mf_set_pair(sc, 0, 1, vc * lc, -(vr * lc), 0, 0, 0, vc * lc + vr * lc);
-        mf_set_pair(sc, 0, 2, vc * bc, vc * br - vr * bc, vr * br, 0, 0,
-                    vc * bc + vr * br + vc * br + vr * bc);
-        mf_set_pair(sc, 1, 2, lc * bc, lc * br, 0, 0, 0, lc * bc + lc * br);
+        for (int idx = 0; idx < 6; ++idx) {
+            int p, q;
+            mf_big_pair_index(idx, p, q);
+            const BlockCoef u = mf_big_pair_coef(idx, hyper + npar);
+            mf_set_pair(sc, p, q, u.cE, u.cAE, u.cGdd, u.cH, u.cG4, u.cW);
+        }
         if (pb.framework == MF_FRAMEWORK_BIGGP_JITT && extra != nullptr)
-            for (int p = 0; p < 3; ++p) sc.jit2[p] = extra[p] * extra[p];
+            for (int p = 0; p < 3; ++p) sc.jit2[p] = dm(extra[p], extra[p]);
     }
 }
 
 // One covariance entry: block (P, Q), epochs (i, j), from the shared bases.
 // `ez` = extra-kernel value at this lag (only read when P == Q and amp2 != 0).
-__device__ __forceinline__ double mf_entry(const SampleCoefs& sc, const Bases& b, int P, int Q,
+template <typename SC>
+__device__ __forceinline__ double mf_entry(const SC& sc, const Bases& b, int P, int Q,
                                            bool same_epoch, double ez, double diag_add,
                                            double nugget) {
     const BlockCoef& c = sc.c[P][Q];

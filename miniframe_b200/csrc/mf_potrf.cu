@@ -32,6 +32,12 @@
 
 #include "mf_common.cuh"
 
+#ifdef MF_EXPERIMENTS
+#define MF_EXPERIMENT_OF(h) ((h)->opt.experiment)
+#else
+#define MF_EXPERIMENT_OF(h) 0
+#endif
+
 namespace pf {
 
 constexpr int TM = 128;       // rows per tile (8 warps x 16)
@@ -48,7 +54,8 @@ constexpr int SZ_DINV = 8 * 64 * 8;                  // minus-inverses of the 8 
 constexpr int SZ_COL = 2 * 72 * 8;                   // double-buffered pivot column: 64 values + status word
 constexpr int SZ_RED = 64 * 8;                       // reduction scratch, next-matrix word, mbarriers, release counters
 constexpr int smem_bytes(int nstage, int nmi = 2) { return nstage * (64 * nmi + NB) * KC * 8 + SZ_LD + SZ_DINV + SZ_COL + SZ_RED + 1024; }
-static_assert(NB * AW_LD * 8 <= 3 * (64 + NB) * KC * 8, "potf2 staging array must fit in the stage area");
+static_assert(NB * AW_LD * 8 <= 3 * (64 + NB) * KC * 8,
+              "potf2 staging array must fit in the stage area");
 // 128-row tiles (NMI = 2): 3 stages, 97,792 B, two CTAs per SM; 64-row tiles (NMI = 1): 73,216 B, three
 
 struct Params {
@@ -71,7 +78,6 @@ struct Params {
                           // ordinal + 1, [3] info of the failure
     double* dinv;
     int* counter;         // next matrix to hand out (one CTA per matrix, zeroed before the launch)
-    long long* trace;     // DBG & 16: per-tile phase timestamps of the first matrix of each CTA
 };
 
 __device__ __forceinline__ double flip(double x) {      // -x on the integer pipe
@@ -129,10 +135,137 @@ __device__ __forceinline__ void fence_async_proxy() {
     asm volatile("fence.proxy.async;" ::: "memory");
 }
 
-// DBG (timing experiments only, results are garbage except for 16): bit mask,
-//   8 = consume the ring without computing, 16 = record per-tile phase timestamps of the
-//   first matrix of every CTA, 32 = skip the diagonal-block factorisation, 64 = skip the
-//   triangular solve, 256 = stream the operands of every matrix from the first four (L2-resident)
+// Factorisation of the 64 x 64 diagonal block C (in Aw, row stride AW_LD) into Ld (8 x 8 blocks)
+// and Dinv (minus the inverses of the diagonal 8 x 8 blocks); a failed pivot is reported through
+// *failword (1-based global index).  Called by all 256 threads; the caller's barrier follows.
+//
+// Warp p owns the 8-column panel p, LEFT-looking, 8 x 8 blocks in the tensor-core accumulator
+// layout (lane 4g + t: row g, columns 2t, 2t + 1):
+//   1. diagonal block (p, p): panels q < p are applied as they are published (one mbarrier per
+//      panel, two DMMAs each), then eight pivots with warp shuffles only - no CTA-wide barrier
+//      per pivot; the critical path of the whole block is 64 x (shuffle, rsqrt, multiply,
+//      shuffle, fma);
+//   2. minus the inverse of the factored diagonal block, eight lanes, one column each;
+//   3. the blocks below it, two at a time: apply the panels q < p, multiply by the inverse
+//      (the same tensor-core triangular solve the row tiles use), store, publish the panel.
+// Register needs stay small (one 8 x 8 block per warp at a time) on purpose: this code shares
+// the register allocation of the contraction loop.
+template <int DBG>
+__device__ __forceinline__ void potf2_panels(const double* Aw, double* Ld, double* Dinv, double* rsbuf,
+                                             uint32_t pbar, volatile int* failword, int nv, int j0,
+                                             uint32_t parity) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const unsigned FULL = 0xffffffffu;
+    const int c0 = 8 * warp + 2 * t;
+    // block (bi, warp) of C, negated (the DMMAs ADD L L^T)
+    auto load_neg = [&](int bi, double& v0, double& v1) {
+        const int r = 8 * bi + g;
+        v0 = flip(Aw[r * AW_LD + c0]);
+        v1 = flip(Aw[r * AW_LD + c0 + 1]);
+    };
+    // columns beyond the matrix order are replaced by the identity once the finished panels have
+    // been applied (the residual row, which follows the last matrix row, would otherwise leak
+    // into them); that keeps the inverses finite and those columns out of every update
+    const bool live0 = c0 < nv, live1 = c0 + 1 < nv;
+    double dg0, dg1;
+    load_neg(warp, dg0, dg1);
+    bool dead = (DBG & 32) != 0;
+    for (int q = 0; q < warp && !dead; ++q) {
+        mbar_wait(pbar + 8 * q, parity);
+        if (*failword) {
+            dead = true;
+            break;
+        }
+        const double2 bq = *reinterpret_cast<const double2*>(Ld + ldblk(warp, q) + g * 8 + 2 * t);
+        dmma884(dg0, dg1, bq.x, bq.x);
+        dmma884(dg0, dg1, bq.y, bq.y);
+    }
+    dg0 = live0 ? flip(dg0) : (8 * warp + g == c0 ? 1.0 : 0.0);
+    dg1 = live1 ? flip(dg1) : (8 * warp + g == c0 + 1 ? 1.0 : 0.0);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        if (dead) break;
+        const double d = __shfl_sync(FULL, (c & 1) ? dg1 : dg0, 4 * c + (c >> 1));
+        if (!DBG && !(d > 0.0)) {           // LAPACK dpotrf pivot test
+            if (lane == 0) *failword = j0 + 8 * warp + c + 1;
+            dead = true;
+            break;
+        }
+        const double rs = rsqrt(d);
+        if (lane == 0) rsbuf[8 * warp + c] = rs;
+        double& col = (c & 1) ? dg1 : dg0;
+        if (t == (c >> 1)) col = (g > c) ? col * rs : (g == c ? d * rs : 0.0);
+        if (c < 7) {
+            // column c at rows 2t, 2t + 1 (the columns this lane updates) and at this lane's row
+            const double l0 = __shfl_sync(FULL, col, 8 * t + (c >> 1));
+            const double l1 = __shfl_sync(FULL, col, 8 * t + 4 + (c >> 1));
+            const double lr = __shfl_sync(FULL, col, 4 * g + (c >> 1));
+            if (2 * t > c && live0) dg0 = fma(-lr, l0, dg0);
+            if (2 * t + 1 > c && live1) dg1 = fma(-lr, l1, dg1);
+        }
+    }
+    if (!dead) {
+        if (2 * t > g) dg0 = 0.0;           // upper part of the diagonal 8 x 8 block
+        if (2 * t + 1 > g) dg1 = 0.0;
+        *reinterpret_cast<double2*>(Ld + ldblk(warp, warp) + g * 8 + 2 * t) = make_double2(dg0, dg1);
+    }
+    __syncwarp();
+    if (!dead && lane < 8) {
+        // column `lane` of MINUS the inverse of the diagonal block (1 / L_ii is the pivot's rsqrt)
+        const double* Lb = Ld + ldblk(warp, warp);
+        double x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double sum = (i == lane) ? -1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < i; ++k) sum -= Lb[i * 8 + k] * x[k];
+            x[i] = sum * rsbuf[8 * warp + i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) Dinv[warp * 64 + i * 8 + lane] = x[i];
+    }
+    __syncwarp();
+    if (!dead) {
+        const double2 dv = *reinterpret_cast<const double2*>(Dinv + warp * 64 + g * 8 + 2 * t);
+        for (int bi = warp + 1; bi < 8; bi += 2) {
+            const bool two = bi + 1 < 8;
+            double a0, a1, b0 = 0.0, b1 = 0.0;
+            load_neg(bi, a0, a1);
+            if (two) load_neg(bi + 1, b0, b1);
+            for (int q = 0; q < warp; ++q) {
+                const double2 bq = *reinterpret_cast<const double2*>(Ld + ldblk(warp, q) + g * 8 + 2 * t);
+                const double2 aq = *reinterpret_cast<const double2*>(Ld + ldblk(bi, q) + g * 8 + 2 * t);
+                dmma884(a0, a1, aq.x, bq.x);
+                dmma884(a0, a1, aq.y, bq.y);
+                if (two) {
+                    const double2 cq = *reinterpret_cast<const double2*>(Ld + ldblk(bi + 1, q) + g * 8 + 2 * t);
+                    dmma884(b0, b1, cq.x, bq.x);
+                    dmma884(b0, b1, cq.y, bq.y);
+                }
+            }
+            if (!live0) a0 = b0 = 0.0;
+            if (!live1) a1 = b1 = 0.0;
+            // a = -(C - sum), dv = -inv(L_pp): x = a dv^T = (C - sum) L_pp^-T
+            double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
+            dmma884(x0, x1, a0, dv.x);
+            dmma884(x0, x1, a1, dv.y);
+            *reinterpret_cast<double2*>(Ld + ldblk(bi, warp) + g * 8 + 2 * t) = make_double2(x0, x1);
+            if (two) {
+                dmma884(y0, y1, b0, dv.x);
+                dmma884(y0, y1, b1, dv.y);
+                *reinterpret_cast<double2*>(Ld + ldblk(bi + 1, warp) + g * 8 + 2 * t) = make_double2(y0, y1);
+            }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(pbar + 8 * warp);       // panel `warp` is in Ld (or the block failed)
+}
+
+// DBG (timing experiments, compiled only with -DMF_EXPERIMENTS; results are garbage): bit mask,
+//   8 = consume the ring without computing, 32 = skip the diagonal-block factorisation,
+//   64 = skip the triangular solve, 128 = do not load the K tiles, 256 = stream the operands
+//   of every matrix from the first four (L2-resident), 512 = do not store the rows of L
 // COOP = 1: `p.group` CTAs (all co-resident: cooperative launch) factorise one matrix together.
 // Inside a block column the row tiles are independent once L_jj is known, so tile `it` goes to
 // CTA (jb + it) mod G of the group; the owner of the diagonal tile publishes L_jj (it is in the
@@ -191,9 +324,13 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
             mbar_init(bar_full + 8 * s0, 1);
             released[s0] = 0;
         }
+        // diagonal-block factorisation: one mbarrier per 8-column panel, the failed-pivot word
+        for (int q = 0; q < 8; ++q) mbar_init(smem_u32(smem + OFF_RED + 320) + 8 * q, 1);
+        *reinterpret_cast<int*>(smem + OFF_RED + 384) = 0;
     }
     __syncthreads();
     uint32_t use_s = 0, use_k = 0;
+    uint32_t potf2_parity = 0;
 
     const int G = COOP ? p.group : 1;
     const int grp = COOP ? (int)blockIdx.x / G : (int)blockIdx.x;
@@ -218,7 +355,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
     // One CTA per matrix: the matrices are handed out through an atomic counter rather than by
     // striding, so a CTA that gets ahead of its neighbour on the SM simply takes more of them and
     // all CTAs finish together.  (Cooperative groups and the timing-experiment builds stride.)
-    constexpr bool DYNAMIC = !COOP && DBG == 0;
+    constexpr bool DYNAMIC = !COOP;
     int* const next_mat = reinterpret_cast<int*>(red + 16);
     for (int mat = grp;; mat += ngroups, ++ordinal) {
         if (DYNAMIC) {
@@ -275,15 +412,6 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 // diagonal tile (triangle blocks s and 7 - s: s + 1 and 8 - s column groups) and in
                 // the ragged last tile of a block column (valid fragments spread round-robin).
                 const int wrow0 = i0 + 8 * tbw;                // first row of fragment 0; fragment 1 is 64 below
-                long long* tr_ = nullptr;
-                if ((DBG & 16) && mat == (int)blockIdx.x && tid == 0) {
-                    int tix = 0;
-                    for (int q = 0; q < jb; ++q) tix += (n + 1 - q * NB + TM - 1) / TM;
-                    tr_ = p.trace + ((size_t)blockIdx.x * 200 + tix + it) * 8;
-                    unsigned smid;
-                    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-                    tr_[0] = smid; tr_[1] = jb * 1000 + it; tr_[2] = clock64();
-                }
                 // 8-column groups this warp has to produce: none if its rows lie beyond the
                 // residual row, only the lower triangle inside the diagonal block
                 int nil0 = (wrow0 > n) ? 0 : nicols;
@@ -346,7 +474,12 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 // accumulators start at -K(tile); the residual enters as row n
                 double acc[2][8][2];
                 const bool interior = (it > 0) && (i0 + TM <= n) && (j0 + NB <= n);
-                if (interior) {
+                if ((DBG & 128) && interior) {
+#pragma unroll
+                    for (int mi = 0; mi < NMI; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < 8; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = -1.0 - (double)lane;
+                } else if (interior) {
 #pragma unroll
                     for (int mi = 0; mi < NMI; ++mi) {
                         const double* src = Kb + (size_t)(wrow0 + 64 * mi + g) * ld + j0 + 2 * t;
@@ -378,7 +511,6 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                     }
                 }
 
-                if ((DBG & 16) && tr_) tr_[3] = clock64();
                 // ---- contraction over the finished columns k < j0 (tensor cores) ----
                 for (int kc = 0; kc < nk; ++kc) {
                     if (DBG & 8) {          // timing experiment: consume the ring without computing
@@ -449,7 +581,6 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                     }
                 }
                 // acc now holds S - K = -C
-                if ((DBG & 16) && tr_) tr_[4] = clock64();
 
                 if (it == 0) {
                     // ---- diagonal block: Cholesky of C[0:64, 0:64], one barrier per column ----
@@ -464,6 +595,27 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                     // these generic-proxy writes land in memory the TMA (async proxy) refills later
                     fence_async_proxy();
                     __syncthreads();
+#ifndef MF_POTF2_OLD
+                    potf2_panels<DBG>(Aw, Ld, Dinv, colbuf, smem_u32(smem + OFF_RED + 320),
+                                      reinterpret_cast<volatile int*>(smem + OFF_RED + 384), nv, j0, potf2_parity);
+                    volatile int* const failword = reinterpret_cast<volatile int*>(smem + OFF_RED + 384);
+                    potf2_parity ^= 1u;
+                    __syncthreads();
+                    if (*failword) {
+                        fail = *failword;
+                        __syncthreads();
+                        if (tid == 0) *failword = 0;
+                    }
+                    if (fail) {
+                        if (COOP && tid == 0) {       // tell the group, then release whoever waits for L_jj
+                            gsync[3] = (unsigned)fail;
+                            __threadfence();
+                            st_release(gsync + 2, ordinal + 1);
+                            st_release(gsync + 1, seq);
+                        }
+                        break;
+                    }
+#else
                     double e[4][4];
 #pragma unroll
                     for (int a = 0; a < 4; ++a)
@@ -539,6 +691,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
 #pragma unroll
                         for (int i = 0; i < 8; ++i) Dinv[bb * 64 + i * 8 + cc] = x[i];
                     }
+#endif
                     // L_jj (and, when the block column is the last one, the z entries that
                     // live inside it) go back to global memory, one 512-byte row per warp pass
 #pragma unroll
@@ -611,7 +764,6 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                     for (int s0 = 0; s0 < NSTAGE; ++s0)
                         if (s0 < nk) tma_chunk((use_s + s0) % NSTAGE, s0, i0 + G * TM);
                 }
-                if ((DBG & 16) && tr_) tr_[5] = clock64();
                 // fragments that still need the solve: real rows, not part of the diagonal block
                 const bool act[2] = {it > 0 && wrow0 <= n, NMI == 2 && wrow0 + 64 <= n};
                 if (!act[0] && !act[1]) continue;
@@ -648,6 +800,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
 #pragma unroll
                 for (int mi = 0; mi < NMI; ++mi) {
                     const int row = wrow0 + 64 * mi + g;
+                    if ((DBG & 512) && row < n - 1) continue;
                     if (act[mi] && row <= n) {
 #pragma unroll
                         for (int ni = 0; ni < 8; ++ni) {
@@ -717,29 +870,26 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
     if (((uintptr_t)K & 15) != 0) MF_FAIL(h, MF_ERR_INVALID, "K must be 16-byte aligned");
     pf::Params p;
     {
-        // tensor map for the TMA ring; cuTensorMapEncodeTiled comes from the driver through
-        // the runtime's entry-point query (no link-time dependency on libcuda)
-        typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                      CUtensorMapFloatOOBfill);
-        static encode_fn encode = nullptr;
-        if (!encode) {
-            void* fn = nullptr;
-            cudaDriverEntryPointQueryResult qres;
-            MF_CUDA_CHECK(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-            if (!fn || qres != cudaDriverEntryPointSuccess) MF_FAIL(h, MF_ERR_CUDA, "cuTensorMapEncodeTiled not available");
-            encode = (encode_fn)fn;
+        // tensor map of the TMA ring, cached per (workspace, shape) in the handle
+        mf_tmap_key key = {1, K, ld, stride, n, batch};
+        mf_tmap_slot* slot = nullptr;
+        const CUtensorMap* tm = mf_tmap_find(h, key, &slot);
+        if (!tm) {
+            mf_tmap_encode_fn encode = mf_tmap_encoder(h);
+            if (!encode) return MF_ERR_CUDA;
+            const cuuint64_t gdim[5] = {(cuuint64_t)ld, 4, 2, (cuuint64_t)(mf_rows_of(n) / 8), (cuuint64_t)batch};
+            const cuuint64_t gstr[4] = {(cuuint64_t)(2 * ld * 8), (cuuint64_t)(ld * 8), (cuuint64_t)(8 * ld * 8),
+                                        (cuuint64_t)(stride * 8)};
+            const cuuint32_t box[5] = {16, 4, 2, 8, 1};
+            const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+            CUresult cr = encode(&slot->map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, K, gdim, gstr, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr != CUDA_SUCCESS) MF_FAIL(h, MF_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)cr);
+            slot->key.kind = key.kind;
+            tm = &slot->map;
         }
-        const cuuint64_t gdim[5] = {(cuuint64_t)ld, 4, 2, (cuuint64_t)(mf_rows_of(n) / 8), (cuuint64_t)batch};
-        const cuuint64_t gstr[4] = {(cuuint64_t)(2 * ld * 8), (cuuint64_t)(ld * 8), (cuuint64_t)(8 * ld * 8),
-                                    (cuuint64_t)(stride * 8)};
-        const cuuint32_t box[5] = {16, 4, 2, 8, 1};
-        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-        CUresult cr = encode(&p.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, K, gdim, gstr, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) MF_FAIL(h, MF_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)cr);
+        p.tmap = *tm;
     }
     p.batch = batch;
     p.n = n;
@@ -757,7 +907,6 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
     p.group = 1;
     p.sync = nullptr;
     p.dinv = nullptr;
-    p.trace = nullptr;
     p.counter = reinterpret_cast<int*>(h->coop_sync);
     // Tile variant.  Small matrices: 64-row tiles (one 8-row fragment per warp, 80 registers) and
     // THREE CTAs per SM.  The 64 sequential pivots per block column are a latency chain that only
@@ -767,9 +916,10 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
     // Larger matrices in batches too small to fill the GPU (cooperative regime) also take the
     // 64-row tiles: twice the tiles to spread over the CTAs of a group (measured: n = 6000, B = 1
     // 26.1 -> 18.3 ms, n = 30000 643 -> 564 ms; break-even near batch x 128-row-tiles = 2.5 x 296).
-    const char* en = getenv("MF_NMI");
+    const int experiment = MF_EXPERIMENT_OF(h);
     const long tiles128 = (long)batch * ((n + 1 + 127) / 128);
-    const bool small_tiles = (en ? atoi(en) == 1 : (n <= 1100 || tiles128 < 5L * h->sm_count)) && !getenv("MF_DBG");
+    const bool small_tiles = (h->opt.potrf_tile ? h->opt.potrf_tile == 1 : (n <= 1100 || tiles128 < 5L * h->sm_count)) &&
+                             experiment == 0;
     const int tile_rows = small_tiles ? 64 : 128;
     const int cta_slots = (small_tiles ? 3 : 2) * h->sm_count;
     const int tile_smem = small_tiles ? pf::smem_bytes(3, 1) : pf::smem_bytes(3);
@@ -785,8 +935,8 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
         const int ntile0 = (n + 1 + tile_rows - 1) / tile_rows;
         int G = coop_slots / batch;
         if (G > ntile0) G = ntile0;
-        const char* eg = getenv("MF_COOP_GROUP");
-        if (eg) G = atoi(eg);
+        const bool forced = h->opt.potrf_group > 0;
+        if (forced) G = h->opt.potrf_group;
         if (G > coop_slots) G = coop_slots;
         if (G > h->coop_groups) G = h->coop_groups;
         // One CTA per SM when that still gives every tile of the first block column its own CTA:
@@ -794,9 +944,9 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
         // which CTAs share an SM cannot be chosen.  (With more tiles than SMs the shared mode
         // wins: n = 30000, one matrix, 148 CTAs 567 ms, 296 or 444 CTAs 500 ms.)
         const int per_sm1 = h->sm_count / batch;          // group size with one CTA per SM
-        const bool alone = !eg && per_sm1 >= 2 && per_sm1 >= ntile0;
+        const bool alone = !forced && per_sm1 >= 2 && per_sm1 >= ntile0;
         if (alone) G = per_sm1 < ntile0 ? per_sm1 : ntile0;
-        if (G >= 2 && !getenv("MF_DBG")) {
+        if (G >= 2 && experiment == 0) {
             int ngroups = (alone ? h->sm_count : coop_slots) / G;
             if (ngroups > batch) ngroups = batch;
             if (ngroups > h->coop_groups) ngroups = h->coop_groups;
@@ -836,34 +986,23 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
                                               pf::smem_bytes(3)));                                 \
         pf::mf_potrf_ll_kernel<3, 2, DBG_, 0, 2><<<grid, pf::THREADS, pf::smem_bytes(3), st>>>(p);    \
     } while (0)
-    // MF_DBG selects one of the timing-experiment instantiations (scripts/gpu_env_sweep.sh,
-    // scripts/trace_run.py); results of those launches are not valid likelihoods
-    const char* ed = getenv("MF_DBG");
-    const int dbg = ed ? atoi(ed) : 0;
-    if (dbg == 16) {
-        const size_t words = (size_t)grid * 200 * 8;
-        MF_CUDA_CHECK(h, cudaMalloc(&p.trace, words * 8));
-        MF_CUDA_CHECK(h, cudaMemsetAsync(p.trace, 0, words * 8, st));
-        MF_LAUNCH(16);
-        MF_CUDA_CHECK(h, cudaStreamSynchronize(st));
-        long long* host = (long long*)malloc(words * 8);
-        MF_CUDA_CHECK(h, cudaMemcpy(host, p.trace, words * 8, cudaMemcpyDeviceToHost));
-        const char* path = getenv("MF_TRACE");
-        FILE* f = fopen(path ? path : "gpurun_out/potrf_trace.bin", "wb");
-        if (f) { fwrite(host, 8, words, f); fclose(f); }
-        free(host);
-        cudaFree(p.trace);
-        return MF_OK;
-    }
-    switch (dbg) {
+#ifdef MF_EXPERIMENTS
+    // timing-experiment instantiations (scripts/ablate.py); their results are not likelihoods
+    switch (experiment) {
+        case 0: MF_LAUNCH(0); break;
         case 8: MF_LAUNCH(8); break;
         case 32: MF_LAUNCH(32); break;
         case 64: MF_LAUNCH(64); break;
         case 96: MF_LAUNCH(96); break;
+        case 128: MF_LAUNCH(128); break;
+        case 224: MF_LAUNCH(224); break;
         case 256: MF_LAUNCH(256); break;
-        case 288: MF_LAUNCH(288); break;
-        default: MF_LAUNCH(0); break;
+        case 736: MF_LAUNCH(736); break;
+        default: MF_FAIL(h, MF_ERR_INVALID, "unknown experiment %d", experiment);
     }
+#else
+    MF_LAUNCH(0);
+#endif
 #undef MF_LAUNCH
     MF_CUDA_CHECK(h, cudaGetLastError());
     return MF_OK;

@@ -1,8 +1,9 @@
-"""Import the UNMODIFIED reference from /root/reference (container only).
+"""Import the UNMODIFIED reference: from /root/reference in the build container, else
+from the copy ``oracle/make_ref.py`` staged under ``oracle/_ref/`` (git-ignored, travels
+to the GPU box).
 
-Test infrastructure.  /root/reference does not exist on the GPU box, so this
-module is only used by ``tests/golden/make_golden.py`` and by the CPU tests
-that are skipped when the reference tree is absent.
+Test infrastructure.  Used by ``tests/golden/make_golden*.py``, by the CPU tests that
+are skipped when no reference tree is present, and by the CPU legs of ``bench.py``.
 
 Two harness-side shims, no edits to the reference:
   1. ``matplotlib`` / ``matplotlib.pyplot`` are not installed, and BIGgp.py:4 /
@@ -18,7 +19,15 @@ import types
 
 import numpy as np
 
-REF_ROOT = os.environ.get("MINIFRAME_REFERENCE", "/root/reference")
+def _find_root():
+    here = os.path.dirname(os.path.abspath(__file__))
+    for root in (os.environ.get("MINIFRAME_REFERENCE"), "/root/reference", os.path.join(here, "_ref")):
+        if root and os.path.isdir(os.path.join(root, "miniframe")):
+            return root
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def available():

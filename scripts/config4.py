@@ -22,7 +22,7 @@ ll = ll.cpu().numpy()
 n = 3 * N
 out = {"config": "BIGgpPlusJitt QP N=%d (n=%d) batch %d, 1 GPU" % (N, n, B), "seconds": dt, "evals_per_s": B / dt,
        "tflops": (n ** 3 / 3 + n ** 2) * B / dt / 1e12, "finite": int(np.isfinite(ll).sum()),
-       "workspace_gb": eng._ws.numel() / 1e9}
+       "workspace_gb": sum(w.numel() for w in eng._ws.values()) / 1e9}
 y = go.biggp_y(rv, rhk, bis)
 errs = []
 for i in (0, B - 1):

