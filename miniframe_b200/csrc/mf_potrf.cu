@@ -512,6 +512,47 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 }
 
                 // ---- contraction over the finished columns k < j0 (tensor cores) ----
+#ifdef MF_FULLTILE
+                // tiles whose sixteen 8 x 8 blocks per warp are all live (every tile strictly inside
+                // the matrix): the same instructions in the same order, without the per-group branches
+                const bool full_tile = (nil0 == 8) && (NMI == 1 || nil1 == 8) && !(DBG & 8);
+                if (full_tile) {
+                    for (int kc = 0; kc < nk; ++kc) {
+                        mbar_wait(bar_full + 8 * use_s, use_k & 1);
+                        const unsigned char* sb = smem + use_s * STAGE_BYTES;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int choff = ((4 * h + t) ^ gp) << 4;
+                            double2 a[2];
+#pragma unroll
+                            for (int mi = 0; mi < NMI; ++mi)
+                                a[mi] = *reinterpret_cast<const double2*>(sb + (8 * tbw + 64 * mi + gp) * 128 + choff);
+#pragma unroll
+                            for (int nq = 0; nq < 2; ++nq) {
+                                double2 b[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u)
+                                    b[u] = *reinterpret_cast<const double2*>(sb + (TM + 8 * (4 * nq + u) + gp) * 128 + choff);
+#pragma unroll
+                                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                                    for (int mi = 0; mi < NMI; ++mi)
+                                        dmma884(acc[mi][4 * nq + u][0], acc[mi][4 * nq + u][1], a[mi].x, b[u].x);
+                                if (h == 1 && nq == 1) release_stage(kc);
+#pragma unroll
+                                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                                    for (int mi = 0; mi < NMI; ++mi)
+                                        dmma884(acc[mi][4 * nq + u][0], acc[mi][4 * nq + u][1], a[mi].y, b[u].y);
+                            }
+                        }
+                        if (++use_s == NSTAGE) {
+                            use_s = 0;
+                            ++use_k;
+                        }
+                    }
+                } else
+#endif
                 for (int kc = 0; kc < nk; ++kc) {
                     if (DBG & 8) {          // timing experiment: consume the ring without computing
                         mbar_wait(bar_full + 8 * use_s, use_k & 1);
@@ -532,6 +573,31 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                         for (int nq = 0; nq < 2; ++nq) {
                             // warp-uniform block-level branches (not per-instruction predicates): they
                             // keep ptxas from hoisting the next group's loads into this group
+#ifdef MF_EXACTDIAG
+                            // diagonal and ragged tiles only (the full tiles take the loop above): every
+                            // 8 x 8 block is issued or skipped on its own, so the triangle of the diagonal
+                            // block costs 36 blocks instead of 48
+                            double2 b[4];
+                            const bool d0 = 4 * nq < nil0, d1 = 4 * nq < nil1;
+                            if (d0 || d1) {
+#pragma unroll
+                                for (int u = 0; u < 4; ++u)
+                                    b[u] = *reinterpret_cast<const double2*>(sb + (TM + 8 * (4 * nq + u) + gp) * 128 + choff);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (4 * nq + u < nil0) dmma884(acc[0][4 * nq + u][0], acc[0][4 * nq + u][1], a[0].x, b[u].x);
+                                if (NMI == 2 && 4 * nq + u < nil1)
+                                    dmma884(acc[NMI - 1][4 * nq + u][0], acc[NMI - 1][4 * nq + u][1], a[NMI - 1].x, b[u].x);
+                            }
+                            if (h == 1 && nq == 1) release_stage(kc);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (4 * nq + u < nil0) dmma884(acc[0][4 * nq + u][0], acc[0][4 * nq + u][1], a[0].y, b[u].y);
+                                if (NMI == 2 && 4 * nq + u < nil1)
+                                    dmma884(acc[NMI - 1][4 * nq + u][0], acc[NMI - 1][4 * nq + u][1], a[NMI - 1].y, b[u].y);
+                            }
+#else
                             double2 b[4];
                             const bool d0 = 4 * nq < nil0, d1 = 4 * nq < nil1;
                             if (d0 || d1) {
@@ -573,6 +639,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
 #pragma unroll
                                 for (int u = 0; u < 4; ++u) dmma884(acc[1][4 * nq + u][0], acc[1][4 * nq + u][1], a[1].y, b[u].y);
                             }
+#endif
                         }
                     }
                     if (++use_s == NSTAGE) {

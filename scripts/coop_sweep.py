@@ -15,7 +15,7 @@ resid = eng.tensor(go.biggp_y(rv, rhk, bis)[None, :])
 for B in Bs:
     H = eng.tensor(go.synthetic_biggp_hypers(B, seed=2))
     for G in Gs:
-        os.environ["MF_COOP_GROUP"] = str(G)
+        eng.set_option("potrf_group", G)
         best = 1e9
         for rep in range(4):
             Kd = eng.build_cov(prob, eng.tensor(t), eng.tensor(gp._diag_yerr()), H, None, full=False)
