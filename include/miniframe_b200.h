@@ -11,7 +11,7 @@
  * Conventions
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
  *     its name ends in _host; the caller owns every data buffer and the
- *     workspace.  mf_create allocates the handle's own 1.2 MB of device scratch
+ *     workspace.  mf_create allocates the handle's own 2 MB of device scratch
  *     (hand-out counter and group barriers of the factorisation); no call after
  *     mf_create allocates, frees or synchronises;
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*;
@@ -96,7 +96,7 @@ typedef struct mf_handle_s* mf_handle_t;
 int  mf_version(void);
 const char* mf_status_string(int status);
 
-/* One handle per (device, stream): it owns 1.2 MB of device scratch (the hand-out
+/* One handle per (device, stream): it owns 2 MB of device scratch (the hand-out
  * counter and the group barriers of mf_potrf_loglike), a small cache of TMA
  * descriptors and the last error text, all of which concurrent launches would
  * share.  Calls on one handle must therefore be issued to one stream at a time;

@@ -78,10 +78,8 @@ extern "C" int mf_create(mf_handle_t* out, int device) {
     h->tmap_next = 0;
     h->coop_groups = 3 * h->sm_count;
     h->coop_sync = nullptr;
-    h->coop_dinv = nullptr;
-    if (cudaMalloc(&h->coop_sync, (size_t)h->coop_groups * 8 * sizeof(unsigned)) != cudaSuccess ||
-        cudaMalloc(&h->coop_dinv, (size_t)h->coop_groups * 512 * sizeof(double)) != cudaSuccess) {
-        cudaFree(h->coop_sync);
+    h->coop_words = 512 * 1024 - 8 * h->coop_groups;
+    if (cudaMalloc(&h->coop_sync, (size_t)(8 * h->coop_groups + h->coop_words) * sizeof(unsigned)) != cudaSuccess) {
         delete h;
         return MF_ERR_CUDA;
     }
@@ -92,7 +90,6 @@ extern "C" int mf_create(mf_handle_t* out, int device) {
 extern "C" int mf_destroy(mf_handle_t h) {
     if (h) {
         cudaFree(h->coop_sync);
-        cudaFree(h->coop_dinv);
     }
     delete h;
     return MF_OK;

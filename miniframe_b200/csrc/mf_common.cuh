@@ -36,13 +36,13 @@ struct mf_handle_s {
     int sm_count;
     int cc_major, cc_minor;
     size_t smem_optin;
-    // Device scratch owned by the handle, allocated once by mf_create (1.2 MB): the hand-out
+    // Device scratch owned by the handle, allocated once by mf_create (2 MB): the hand-out
     // counter of the persistent factorisation and, for its cooperative variant (several CTAs per
-    // matrix), per group 8 synchronisation words and the 8 negated 8x8 inverses (512 doubles).
-    // Launches on one handle share it: one handle per stream.
+    // matrix), per group 8 synchronisation words followed by the pool of `rowdone` words (one per
+    // 64-row block of the group's matrix).  Launches on one handle share it: one handle per stream.
     unsigned* coop_sync;
-    double* coop_dinv;
     int coop_groups;
+    int coop_words;           // words in the rowdone pool (behind the 8 x coop_groups header words)
     mf_options opt;
     mf_tmap_slot tmaps[MF_TMAP_SLOTS];
     int tmap_next;

@@ -72,11 +72,12 @@ struct Params {
     double* ll;
     int32_t* info;
     int sm_count;
-    // cooperative variant (COOP): `group` CTAs share one matrix; 8 words + 512 doubles per group
+    // cooperative variant (COOP): `group` CTAs share one matrix
     int group;
-    unsigned* sync;       // [0] barrier arrivals, [1] diagonal-block sequence number, [2] failed matrix
-                          // ordinal + 1, [3] info of the failure
-    double* dinv;
+    unsigned* sync;       // per group 8 words: [0] barrier arrivals, [2] failed matrix ordinal + 1,
+                          // [3] info of the failure
+    unsigned* rowdone;    // per group rd_stride words: block columns finished per 64-row block
+    int rd_stride;
     int* counter;         // next matrix to hand out (one CTA per matrix, zeroed before the launch)
 };
 
@@ -133,6 +134,26 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
 }
 __device__ __forceinline__ void fence_async_proxy() {
     asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+// MINUS the inverses of the eight diagonal 8 x 8 blocks of L_jj (in Ld), the operand of the row
+// tiles' triangular solve: thread 8 bb + cc computes column cc of block bb.  One routine for the
+// CTA that factorised L_jj and for the CTAs that fetched it: the same bits everywhere.
+__device__ __forceinline__ void dinv_blocks(const double* Ld, double* Dinv, int tid) {
+    if (tid < 64) {
+        const int bb = tid >> 3, cc = tid & 7;
+        const double* Lb = Ld + ldblk(bb, bb);
+        double x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double sum = (i == cc) ? -1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < i; ++k) sum -= Lb[i * 8 + k] * x[k];
+            x[i] = sum / Lb[i * 8 + i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) Dinv[bb * 64 + i * 8 + cc] = x[i];
+    }
 }
 
 // Factorisation of the 64 x 64 diagonal block C (in Aw, row stride AW_LD) into Ld (8 x 8 blocks)
@@ -266,14 +287,20 @@ __device__ __forceinline__ void potf2_panels(const double* Aw, double* Ld, doubl
 //   8 = consume the ring without computing, 32 = skip the diagonal-block factorisation,
 //   64 = skip the triangular solve, 128 = do not load the K tiles, 256 = stream the operands
 //   of every matrix from the first four (L2-resident), 512 = do not store the rows of L
-// COOP = 1: `p.group` CTAs (all co-resident: cooperative launch) factorise one matrix together.
-// Inside a block column the row tiles are independent once L_jj is known, so tile `it` goes to
-// CTA (jb + it) mod G of the group; the owner of the diagonal tile publishes L_jj (it is in the
-// matrix) and the 8x8 inverses through global memory and a sequence number, the others contract
-// their tiles first and pick L_jj up just before their triangular solve.  One group barrier
-// (atomic counter, release/acquire) per block column orders the rows written by the other CTAs
-// before the TMA loads of the next block column.  Few large matrices (n = 30000, B = 1 or 64) or
-// a small ensemble then fill the GPU instead of one SM per matrix.
+// COOP = 1: `p.group` CTAs (all co-resident: cooperative launch) factorise one matrix together,
+// as a DATAFLOW over row tiles: tile `it` of block column jb goes to CTA (jb + it) mod G, every
+// CTA walks its tiles in order, and there is no barrier between block columns.  A tile needs
+// (i) its own rows and the block column's diagonal rows finished through the columns a chunk
+// reads - the CTA that issues the chunk's TMA load first waits for `rowdone` of those 64-row
+// blocks (one monotone word per row block: block columns finished, release/acquire; the check
+// is a register compare once a row block is known to be complete) - and (ii) L_jj for its
+// triangular solve, which is the diagonal tile's rowdone word.  CTAs that have no tile left in a
+// block column run ahead into the next ones, up to the chunks that do depend on unfinished rows:
+// the tail of a large matrix (fewer tiles than CTAs, long contractions) keeps all SMs busy.
+// Per-element arithmetic is the one-CTA-per-matrix order (the factor is bit-identical); the
+// minus-inverses of L_jj's diagonal blocks are recomputed by every CTA from L_jj with the same
+// routine.  One group barrier per MATRIX.  Few large matrices (n = 30000, B = 1 or 64) or a small
+// ensemble then fill the GPU instead of one SM per matrix.
 template <int NSTAGE, int MINB, int DBG, int COOP, int NMI>
 __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid_constant__ Params p) {
     // NMI 8-row fragments per warp: tiles of 64 * NMI rows (NMI = 1: 80 registers, three CTAs per SM)
@@ -337,7 +364,11 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
     const int rank = COOP ? (int)blockIdx.x % G : 0;
     const int ngroups = COOP ? (int)gridDim.x / G : (int)gridDim.x;
     unsigned* const gsync = COOP ? p.sync + 8 * grp : nullptr;
-    double* const gdinv = COOP ? p.dinv + 512 * grp : nullptr;
+    unsigned* const grow = COOP ? p.rowdone + (size_t)grp * p.rd_stride : nullptr;
+    // block columns known to be finished for the rows of the current tile / for the diagonal rows
+    // of the current block column (CTA-wide cache of rowdone, so that most chunk issues cost a
+    // shared-memory compare) and the level this thread has fenced into the async proxy
+    volatile int* const known = reinterpret_cast<volatile int*>(smem + OFF_RED + 400);
     unsigned bar_target = 0;          // arrivals that complete the next group barrier
     unsigned ordinal = 0;             // matrices this group has started before this one
     auto group_barrier = [&]() {
@@ -350,6 +381,17 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
             }
         }
         __syncthreads();
+    };
+
+    // rows a tile has finished are announced (rowdone) at the next CTA-wide barrier after it
+    int pend_rb = 0, pend_n = 0;
+    unsigned pend_val = 0;
+    auto publish_pending = [&]() {
+        if (pend_n > 0 && tid == 0) {
+            __threadfence();
+            for (int k = 0; k < pend_n; ++k) st_release(grow + pend_rb + k, pend_val);
+        }
+        pend_n = 0;
     };
 
     // One CTA per matrix: the matrices are handed out through an atomic counter rather than by
@@ -377,13 +419,10 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
         }
 
         for (int jb = 0; jb < ncb; ++jb) {
-            if (COOP && jb > 0) {
-                // rows of the previous block column, written by every CTA of the group, are visible
-                // from here on; a failed pivot is learnt here by the CTAs that did not meet it
-                group_barrier();
-                if (ld_acquire(gsync + 2) == ordinal + 1) fail = (int)ld_acquire(gsync + 3);
-            }
-            if (fail) break;
+            // a failed pivot is learnt here by the CTAs that did not meet it (one thread looks, the
+            // barrier below makes the answer the same for the whole CTA)
+            if (COOP && tid == 0)
+                known[3] = (jb > 0 && ld_acquire(gsync + 2) == ordinal + 1) ? (int)ld_acquire(gsync + 3) : 0;
             const int j0 = jb * NB;
             const int nv = min(NB, n - j0);
             const int ntile = (n + 1 - j0 + TM - 1) / TM;
@@ -393,6 +432,8 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
             // memory before anyone prefetches them (the first chunks are issued ahead of
             // the first barrier of the contraction loop); also fences the stage area
             __syncthreads();
+            if (COOP && known[3]) fail = known[3];
+            if (fail) break;
             // The rows of L this block column streams were written through the generic proxy by
             // all threads (ordered by the barrier above); a thread that issues TMA loads must
             // itself order them before its async-proxy reads, and any warp's lane 0 may be the
@@ -401,9 +442,20 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
             // matrices of a full wave come out wrong.)
             fence_async_proxy();
 
+            if (COOP) publish_pending();      // (the barrier above: the last tile of the previous block column is complete)
             const int it_first = COOP ? (rank - jb % G + G) % G : 0;
-            const unsigned seq = ordinal * (unsigned)ncb + (unsigned)jb + 1u;
+            const unsigned seq0 = ordinal * (unsigned)(ncb + 2);      // rowdone = seq0 + finished block columns
             bool have_L = !COOP;
+            if (COOP && tid == 0) known[1] = 0;                        // diagonal rows of this block column
+            // rowdone of row block `rbk` has reached `cols` finished block columns (polled by ONE
+            // thread; gives up when the matrix has failed - the chunk is then issued regardless,
+            // the ring must stay in step)
+            auto wait_rows = [&](int rbk, int cols) -> int {
+                unsigned v;
+                while ((int)((v = ld_acquire(grow + rbk)) - (seq0 + (unsigned)cols)) < 0)
+                    if (ld_acquire(gsync + 2) == ordinal + 1) return cols;
+                return (int)(v - seq0);
+            };
             for (int it = it_first; it < ntile; it += G) {
                 const int i0 = j0 + it * TM;
                 // Rows of the tile are dealt to the warps in 8-row fragments: fragment mi of warp w
@@ -417,12 +469,47 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 int nil0 = (wrow0 > n) ? 0 : nicols;
                 const int nil1 = (NMI < 2 || wrow0 + 64 > n) ? 0 : nicols;
                 if (it == 0) nil0 = min(nil0, tbw + 1);
+                int fenced = 0;                                        // per thread, per tile
+                if (COOP) {
+                    // every warp is done with the previous tile: its rows are final
+                    __syncthreads();
+                    publish_pending();
+                    // the ring tail of the previous tile looked the rows of THIS tile up in slot 2
+                    if (tid == 0) {
+                        known[0] = (it == it_first) ? 0 : known[2];
+                        known[2] = 0;
+                    }
+                    __syncthreads();
+                    // rows this tile finishes: the row blocks below the diagonal block
+                    pend_rb = (i0 >> 6) + (it == 0 ? 1 : 0);
+                    pend_n = NMI - (it == 0 ? 1 : 0);
+                    pend_val = seq0 + (unsigned)jb + 1u;
+                }
 
                 // put chunk kc of the row tile at r0 into stage st: three 64-row TMA boxes, issued by
                 // one thread (rows beyond the allocation are zero-filled by the hardware)
                 auto tma_chunk = [&](uint32_t st, int kc, int r0) {
                     const uint32_t bar = bar_full + 8 * st;
                     const uint32_t dst = stage_u32 + st * STAGE_BYTES;
+                    if (COOP) {
+                        // columns 16 kc .. of block column c: the tile's rows and the diagonal rows
+                        // must be finished through c + 1 block columns
+                        const int need = (kc * KC) / NB + 1;
+                        const int slot = (r0 == i0) ? 0 : 2;          // this tile / the CTA's next tile
+                        int have = min((int)known[slot], (int)known[1]);
+                        if (have < need) {
+                            int a = wait_rows(r0 >> 6, need);
+                            if (NMI == 2 && r0 + 64 <= n) a = min(a, wait_rows((r0 >> 6) + 1, need));
+                            const int b = wait_rows(jb, need);
+                            known[slot] = a;
+                            known[1] = b;
+                            have = min(a, b);
+                        }
+                        if (fenced < need) {
+                            fence_async_proxy();                       // acquired rows -> this thread's TMA reads
+                            fenced = have;
+                        }
+                    }
                     mbar_expect_tx(bar, STAGE_BYTES);
                     const int lmat = (DBG & 256) ? (mat & 3) : mat;
                     // the rows of the tile are streamed once, the block column's own rows are read
@@ -512,47 +599,6 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 }
 
                 // ---- contraction over the finished columns k < j0 (tensor cores) ----
-#ifdef MF_FULLTILE
-                // tiles whose sixteen 8 x 8 blocks per warp are all live (every tile strictly inside
-                // the matrix): the same instructions in the same order, without the per-group branches
-                const bool full_tile = (nil0 == 8) && (NMI == 1 || nil1 == 8) && !(DBG & 8);
-                if (full_tile) {
-                    for (int kc = 0; kc < nk; ++kc) {
-                        mbar_wait(bar_full + 8 * use_s, use_k & 1);
-                        const unsigned char* sb = smem + use_s * STAGE_BYTES;
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int choff = ((4 * h + t) ^ gp) << 4;
-                            double2 a[2];
-#pragma unroll
-                            for (int mi = 0; mi < NMI; ++mi)
-                                a[mi] = *reinterpret_cast<const double2*>(sb + (8 * tbw + 64 * mi + gp) * 128 + choff);
-#pragma unroll
-                            for (int nq = 0; nq < 2; ++nq) {
-                                double2 b[4];
-#pragma unroll
-                                for (int u = 0; u < 4; ++u)
-                                    b[u] = *reinterpret_cast<const double2*>(sb + (TM + 8 * (4 * nq + u) + gp) * 128 + choff);
-#pragma unroll
-                                for (int u = 0; u < 4; ++u)
-#pragma unroll
-                                    for (int mi = 0; mi < NMI; ++mi)
-                                        dmma884(acc[mi][4 * nq + u][0], acc[mi][4 * nq + u][1], a[mi].x, b[u].x);
-                                if (h == 1 && nq == 1) release_stage(kc);
-#pragma unroll
-                                for (int u = 0; u < 4; ++u)
-#pragma unroll
-                                    for (int mi = 0; mi < NMI; ++mi)
-                                        dmma884(acc[mi][4 * nq + u][0], acc[mi][4 * nq + u][1], a[mi].y, b[u].y);
-                            }
-                        }
-                        if (++use_s == NSTAGE) {
-                            use_s = 0;
-                            ++use_k;
-                        }
-                    }
-                } else
-#endif
                 for (int kc = 0; kc < nk; ++kc) {
                     if (DBG & 8) {          // timing experiment: consume the ring without computing
                         mbar_wait(bar_full + 8 * use_s, use_k & 1);
@@ -573,31 +619,6 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                         for (int nq = 0; nq < 2; ++nq) {
                             // warp-uniform block-level branches (not per-instruction predicates): they
                             // keep ptxas from hoisting the next group's loads into this group
-#ifdef MF_EXACTDIAG
-                            // diagonal and ragged tiles only (the full tiles take the loop above): every
-                            // 8 x 8 block is issued or skipped on its own, so the triangle of the diagonal
-                            // block costs 36 blocks instead of 48
-                            double2 b[4];
-                            const bool d0 = 4 * nq < nil0, d1 = 4 * nq < nil1;
-                            if (d0 || d1) {
-#pragma unroll
-                                for (int u = 0; u < 4; ++u)
-                                    b[u] = *reinterpret_cast<const double2*>(sb + (TM + 8 * (4 * nq + u) + gp) * 128 + choff);
-                            }
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                if (4 * nq + u < nil0) dmma884(acc[0][4 * nq + u][0], acc[0][4 * nq + u][1], a[0].x, b[u].x);
-                                if (NMI == 2 && 4 * nq + u < nil1)
-                                    dmma884(acc[NMI - 1][4 * nq + u][0], acc[NMI - 1][4 * nq + u][1], a[NMI - 1].x, b[u].x);
-                            }
-                            if (h == 1 && nq == 1) release_stage(kc);
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                if (4 * nq + u < nil0) dmma884(acc[0][4 * nq + u][0], acc[0][4 * nq + u][1], a[0].y, b[u].y);
-                                if (NMI == 2 && 4 * nq + u < nil1)
-                                    dmma884(acc[NMI - 1][4 * nq + u][0], acc[NMI - 1][4 * nq + u][1], a[NMI - 1].y, b[u].y);
-                            }
-#else
                             double2 b[4];
                             const bool d0 = 4 * nq < nil0, d1 = 4 * nq < nil1;
                             if (d0 || d1) {
@@ -639,7 +660,6 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
 #pragma unroll
                                 for (int u = 0; u < 4; ++u) dmma884(acc[1][4 * nq + u][0], acc[1][4 * nq + u][1], a[1].y, b[u].y);
                             }
-#endif
                         }
                     }
                     if (++use_s == NSTAGE) {
@@ -650,8 +670,14 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 // acc now holds S - K = -C
 
                 if (it == 0) {
-                    // ---- diagonal block: Cholesky of C[0:64, 0:64], one barrier per column ----
+                    // ---- diagonal block: Cholesky of C[0:64, 0:64] ----
+                    // (a CTA that ran ahead of a failed block column must not factorise garbage)
+                    if (COOP && tid == 0) known[3] = (ld_acquire(gsync + 2) == ordinal + 1) ? (int)ld_acquire(gsync + 3) : 0;
                     __syncthreads();              // every warp is done with the stages Aw aliases
+                    if (COOP && known[3]) {
+                        fail = known[3];
+                        break;
+                    }
                     // fragment 0 of every warp is its 8-row block of the diagonal block
 #pragma unroll
                     for (int ni = 0; ni < 8; ++ni) {
@@ -678,7 +704,6 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                             gsync[3] = (unsigned)fail;
                             __threadfence();
                             st_release(gsync + 2, ordinal + 1);
-                            st_release(gsync + 1, seq);
                         }
                         break;
                     }
@@ -733,7 +758,6 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                             gsync[3] = (unsigned)fail;
                             __threadfence();
                             st_release(gsync + 2, ordinal + 1);
-                            st_release(gsync + 1, seq);
                         }
                         break;
                     }
@@ -743,22 +767,10 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                             if ((tid >> 3) >= (c >> 3))
                                 Ld[ldblk(tid >> 3, c >> 3) + (tid & 7) * 8 + (c & 7)] = (tid == c) ? 1.0 : 0.0;
                     __syncthreads();
-                    if (tid < 64) {
-                        // column cc of MINUS the inverse of the 8x8 diagonal block bb of L_jj
-                        const int bb = tid >> 3, cc = tid & 7;
-                        const double* Lb = Ld + ldblk(bb, bb);
-                        double x[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            double sum = (i == cc) ? -1.0 : 0.0;
-#pragma unroll
-                            for (int k = 0; k < i; ++k) sum -= Lb[i * 8 + k] * x[k];
-                            x[i] = sum / Lb[i * 8 + i];
-                        }
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) Dinv[bb * 64 + i * 8 + cc] = x[i];
-                    }
 #endif
+                    // the inverses the row tiles multiply by (the factorisation above kept its own,
+                    // built from the pivots' reciprocal square roots, for the blocks inside L_jj)
+                    dinv_blocks(Ld, Dinv, tid);
                     // L_jj (and, when the block column is the last one, the z entries that
                     // live inside it) go back to global memory, one 512-byte row per warp pass
 #pragma unroll
@@ -779,24 +791,21 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                     }
                     fence_async_proxy();          // L_jj -> async proxy
                     __syncthreads();
-                    if (COOP) {
-                        // publish: L_jj is in the matrix, the inverses go to the group's scratch
-                        gdinv[tid] = Dinv[tid];
-                        gdinv[tid + THREADS] = Dinv[tid + THREADS];
+                    if (COOP && tid == 0) {
+                        // publish: the rows of L_jj are final (row block jb has jb + 1 block columns)
                         __threadfence();
-                        __syncthreads();
-                        if (tid == 0) st_release(gsync + 1, seq);
+                        st_release(grow + jb, seq0 + (unsigned)jb + 1u);
                     }
                     have_L = true;
                 } else if (COOP && !have_L) {
                     // first tile of a CTA that does not own the diagonal block: wait for it
                     if (tid == 0) {
-                        while ((int)(ld_acquire(gsync + 1) - seq) < 0) {
-                        }
+                        wait_rows(jb, jb + 1);
+                        known[3] = (ld_acquire(gsync + 2) == ordinal + 1) ? (int)ld_acquire(gsync + 3) : 0;
                     }
                     __syncthreads();
-                    if (ld_acquire(gsync + 2) == ordinal + 1) {
-                        fail = (int)ld_acquire(gsync + 3);
+                    if (known[3]) {
+                        fail = known[3];
                         // the tail of this tile has already put the first chunks of this CTA's next
                         // tile into the ring: take them out again so the ring stays in step
                         if (it + G < ntile && nk > 0) {
@@ -818,8 +827,8 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                         Ld[idx] = (r < nv && c < nv) ? __ldcg(Kb + (size_t)(j0 + r) * ld + j0 + c)
                                                      : (r == c ? 1.0 : 0.0);
                     }
-                    Dinv[tid] = __ldcg(gdinv + tid);
-                    Dinv[tid + THREADS] = __ldcg(gdinv + tid + THREADS);
+                    __syncthreads();
+                    dinv_blocks(Ld, Dinv, tid);
                     __syncthreads();
                     have_L = true;
                 }
@@ -888,6 +897,8 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
         // z (row n) and the diagonal of L are read back in one fixed order, whoever wrote them:
         // the result is bit-identical for one CTA per matrix and for any cooperative group size.
         if (COOP) {
+            __syncthreads();
+            publish_pending();
             group_barrier();          // the other CTAs' rows are complete and visible
             if (!fail && ld_acquire(gsync + 2) == ordinal + 1) fail = (int)ld_acquire(gsync + 3);
             if (rank != 0) continue;  // CTA 0 of the group finishes alone
@@ -973,7 +984,8 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
     cudaStream_t st = (cudaStream_t)stream;
     p.group = 1;
     p.sync = nullptr;
-    p.dinv = nullptr;
+    p.rowdone = nullptr;
+    p.rd_stride = 0;
     p.counter = reinterpret_cast<int*>(h->coop_sync);
     // Tile variant.  Small matrices: 64-row tiles (one 8-row fragment per warp, 80 registers) and
     // THREE CTAs per SM.  The 64 sequential pivots per block column are a latency chain that only
@@ -1013,16 +1025,21 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
         const int per_sm1 = h->sm_count / batch;          // group size with one CTA per SM
         const bool alone = !forced && per_sm1 >= 2 && per_sm1 >= ntile0;
         if (alone) G = per_sm1 < ntile0 ? per_sm1 : ntile0;
-        if (G >= 2 && experiment == 0) {
+        // one rowdone word per 64-row block (the residual row included) and group
+        const int rd_stride = (n + 1 + 63) / 64 + 2;
+        if (G >= 2 && experiment == 0 && rd_stride <= h->coop_words) {
             int ngroups = (alone ? h->sm_count : coop_slots) / G;
             if (ngroups > batch) ngroups = batch;
             if (ngroups > h->coop_groups) ngroups = h->coop_groups;
+            if (ngroups > h->coop_words / rd_stride) ngroups = h->coop_words / rd_stride;
             // a dynamic shared-memory request above half an SM keeps a second CTA off the SM
             const int smem = alone ? 120 * 1024 : tile_smem;
             p.group = G;
             p.sync = h->coop_sync;
-            p.dinv = h->coop_dinv;
-            MF_CUDA_CHECK(h, cudaMemsetAsync(h->coop_sync, 0, (size_t)h->coop_groups * 8 * sizeof(unsigned), st));
+            p.rowdone = h->coop_sync + 8 * h->coop_groups;
+            p.rd_stride = rd_stride;
+            MF_CUDA_CHECK(h, cudaMemsetAsync(h->coop_sync, 0,
+                                             ((size_t)8 * h->coop_groups + (size_t)ngroups * rd_stride) * sizeof(unsigned), st));
             MF_CUDA_CHECK(h, cudaFuncSetAttribute(coop_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
             void* args[] = {(void*)&p};
             const cudaError_t ce = cudaLaunchCooperativeKernel(coop_fn, dim3(ngroups * G), dim3(pf::THREADS), args,

@@ -10,7 +10,8 @@ from miniframe_b200.BIGgpPlusJitt import BIGgp as BIGgpJ
 from oracle import gp_oracle as go
 
 bad = 0
-for N, B, reps in [(100, 2368, 6), (333, 1184, 6), (500, 1776, 6), (500, 100, 10), (500, 7, 10), (700, 592, 4), (1000, 40, 4), (43, 4096, 6)]:
+for N, B, reps in [(100, 2368, 6), (333, 1184, 6), (500, 1776, 6), (500, 100, 10), (500, 7, 10), (200, 9, 30), (200, 1, 30),
+                   (700, 592, 4), (1000, 40, 4), (2000, 3, 4), (43, 4096, 6), (21, 50, 20)]:
     t, (rv, rhk, bis), (e1, e2, e3) = go.synthetic_series(N, seed=N)
     H = go.synthetic_biggp_hypers(B, seed=B)
     J = go.synthetic_jitter(B, seed=B)
