@@ -109,6 +109,8 @@ int  mf_device_info(mf_handle_t h, int* sm_count, int* cc_major, int* cc_minor);
 /* Tuning / test knobs of one handle (0 restores the library's own choice):
  *   "potrf_tile"   1: 64-row tiles, 2: 128-row tiles of the factorisation
  *   "potrf_group"  1: one CTA per matrix, G > 1: G CTAs per matrix (cooperative)
+ *   "potrf_map"    cooperative factorisation, which CTA takes which row tile:
+ *                  1: (tile - block column) mod G, 2: (tile + block column) mod G
  *   "cov_ctas"     CTAs per sample of the covariance build
  *   "experiment"   timing-experiment variants; rejected with MF_ERR_UNSUPPORTED
  *                  unless the library was built with -DMF_EXPERIMENTS (the
@@ -213,13 +215,31 @@ int mf_solve_logdet(mf_handle_t h, int batch, int n,
                     double* z, double* ll, const int32_t* info, void* stream);
 
 /*
+ * Gradient of the log-likelihood with respect to the hyper-parameters (not in the
+ * reference; the consumer would be an optimiser or HMC on minus_log_likelihood,
+ * BIGgp.py:315-317):  grad[b][k] = -1/2 sum_{R,C} W_b[R][C] dK_b[R][C]/dtheta_k  with
+ * W = K^-1 - alpha alpha^T, alpha = K^-1 r.  The caller supplies W (e.g. from the
+ * factor mf_loglike leaves in the workspace); dK/dtheta is evaluated on the fly from t
+ * and the hyper-parameters and never stored.  BIGgp / BIGgpPlusJitt.
+ *   W        [batch] symmetric matrices in the EPOCH-INTERLEAVED order (row 3 i + P),
+ *            leading dimension ld, `stride` doubles apart; only the lower triangle is read
+ *   partial  scratch, batch x mf_grad_ctas(n_epochs) x 24 doubles
+ *   grad     [batch x (hyper_len + extra_len)]: d ll / d(kernel pars, vc vr lc bc br, jitters)
+ */
+int mf_grad_ctas(int n_epochs);
+int mf_grad_contract(mf_handle_t h, const mf_problem_t* prob, int batch,
+                     const double* t, const double* hyper, const double* extra,
+                     const double* W, int64_t ld, int64_t stride,
+                     double* partial, double* grad, void* stream);
+
+/*
  * Diagnostics: register-resident FP64 throughput probes used as roofline
  * denominators (mode 0: mma.sync m8n8k4 f64 "DMMA", mode 1: DFMA).  Runs
  * `iters` inner iterations on every SM, returns the elapsed milliseconds of the
  * launch and the floating-point operations it executed.
  */
 int mf_probe_fp64(mf_handle_t h, int mode, int iters, float* ms_host, double* flops_host,
-                  void* stream);
+                  void* stream);   /* times itself: creates events and synchronises the stream */
 
 #ifdef __cplusplus
 }

@@ -179,6 +179,24 @@ class BIGgp(GPBase):
     def minus_log_likelihood(self, a, b, nugget=True):
         return -self.log_likelihood(a, b, nugget=True)
 
+    # ---- gradient (not in the reference) -------------------------
+    def log_likelihood_grad_batch(self, A, Bm=None):
+        """(ll (B,), d ll / d A (B, 9 | 7)) for the rows of ``A``: what an optimiser or HMC on
+        ``minus_log_likelihood`` (reference BIGgp.py:315-317) needs.  See GPBase._batch_loglike_grad."""
+        if not _is_torch(A):
+            A = np.asarray(A, dtype=float)
+        key, make = self._diag(True)
+        return self._batch_loglike_grad(self._problem(self.t.size), key, make, A, None, Bm)
+
+    def log_likelihood_grad(self, a, b):
+        """(log_likelihood(a, b), its gradient with respect to ``a``)."""
+        self.mean_pars = b
+        hyper = self._hyper_row(a)
+        self._check_finite(hyper)
+        ll, g = self.log_likelihood_grad_batch(hyper, np.asarray(self._mean_pars, dtype=float)[None, :]
+                                               if self.mean_pars_size else None)
+        return float(ll[0]), g[0]
+
     # ---- sampling (reference BIGgp.py:320-378) --------------------------------------------
     def _draw(self, K, n, size, seed):
         """x = L xi with K = L L^T from the factorisation kernel and xi ~ N(0, I) drawn on the

@@ -40,6 +40,27 @@ class BIGgp(_plain.BIGgp):
             raise TypeError("log_likelihood() missing 1 required positional argument: 'c'")
         return -self.log_likelihood(a, b, c, nugget=True)
 
+    def log_likelihood_grad_batch(self, A, Bm=None, C=None):
+        """(ll (B,), gradient (B, 9 | 7 + 3)): columns follow ``A`` and then the jitters ``C``."""
+        if C is None:
+            raise TypeError("log_likelihood_grad_batch() needs the jitters C of shape (B, 3)")
+        if not _is_torch(A):
+            A = np.asarray(A, dtype=float)
+        if not _is_torch(C):
+            C = np.asarray(C, dtype=float)
+        key, make = self._diag(True)
+        return self._batch_loglike_grad(self._problem(self.t.size, jitter=True), key, make, A, C, Bm)
+
+    def log_likelihood_grad(self, a, b, c):
+        """(log_likelihood(a, b, c), its gradient with respect to [a, c])."""
+        self.mean_pars = b
+        hyper = self._hyper_row(a)
+        jit = np.asarray(c, dtype=float).ravel()[None, :3]
+        self._check_finite(hyper, jit)
+        ll, g = self.log_likelihood_grad_batch(hyper, np.asarray(self._mean_pars, dtype=float)[None, :]
+                                               if self.mean_pars_size else None, jit)
+        return float(ll[0]), g[0]
+
     def sample(self, a, j=None, size=None, seed=None):
         """Draw from N(0, compute_matrix(a, j)).  The reference's sample(a) forwards only ``a`` to
         compute_matrix(a, j) and so raises TypeError (BIGgpPlusJitt.py:326-341); the same happens

@@ -154,6 +154,85 @@ class GPBase(object):
             if x is not None and not np.all(np.isfinite(x)):
                 raise ValueError("array must not contain infs or NaNs")
 
+    def _batch_loglike_grad(self, prob, diag_key, diag_make, A, extra, Bm):
+        """Log-likelihood and its gradient with respect to the rows of ``A`` (and of ``extra``: the
+        jitters); returns (ll (B,), grad (B, hyper_len + extra_len)) of the
+        kind of ``A``.  The reference has no gradient; its consumer would be an optimiser on
+        minus_log_likelihood (BIGgp.py:315-317).
+
+            d ll / d theta = -1/2 sum W dK/dtheta,   W = K^-1 - alpha alpha^T,   alpha = K^-1 r
+
+        The factor comes from the likelihood path itself (it stays in the workspace, in the
+        epoch-interleaved order), alpha and K^-1 from the library's triangular routines on that
+        factor, and the contraction with dK/dtheta - which is never formed - from the hand-written
+        kernel mf_grad_contract.  Samples whose covariance is not positive definite give -inf and a
+        NaN gradient."""
+        import ctypes
+        import torch
+        if prob.framework == _lib.FRAMEWORK_SMALLGP or prob.nugget != 0.0:
+            raise NotImplementedError("the gradient is built for BIGgp / BIGgpPlusJitt")
+        eng = self.engine
+        want_torch = _is_torch(A)
+        hyper = eng.tensor(A)
+        if hyper.ndim != 2 or hyper.shape[1] != prob.hyper_len:
+            raise ValueError("expected hyper-parameters of shape (B, %d), got %s"
+                             % (prob.hyper_len, tuple(hyper.shape)))
+        B = hyper.shape[0]
+        ex = None
+        if prob.extra_len:
+            ex = eng.tensor(extra)
+            if ex.ndim != 2 or ex.shape != (B, prob.extra_len):
+                raise ValueError("expected extra parameters of shape (%d, %d)" % (B, prob.extra_len))
+        if self.mean_pars_size == 0:
+            resid = self._dev("resid_no_mean_pars", lambda: self._residual_rows(None, B))
+        else:
+            if Bm is None:
+                raise ValueError("this model has %d mean parameters: pass one row per sample"
+                                 % self.mean_pars_size)
+            resid = self._residual_rows_device(Bm, B)
+            if resid is None:
+                resid = eng.tensor(self._residual_rows(Bm, B))
+        t = self._dev("t", lambda: np.asarray(self.t, dtype=float))
+        diag = self._dev(diag_key, diag_make)
+        M, N = prob.n_series, prob.n_epochs
+        n = M * N
+        r = torch.arange(n, device=eng.device)
+        perm = (r % M) * N + r // M                    # interleaved row r = M i + P  <-  P N + i
+        npar = prob.hyper_len + prob.extra_len
+        ll = torch.empty(B, dtype=torch.float64, device=eng.device)
+        grad = torch.empty((B, npar), dtype=torch.float64, device=eng.device)
+        info = torch.empty(B, dtype=torch.int32, device=eng.device)
+        ld, stride = eng.ld(n), eng.matrix_stride(n)
+        free, _ = torch.cuda.mem_get_info(eng.device)
+        chunk = max(1, min(B, int(0.2 * free) // (stride * 8 + 3 * n * n * 8)))
+        ctas = int(eng.lib.mf_grad_ctas(N))
+        for b0 in range(0, B, chunk):
+            nb = min(chunk, B - b0)
+            sub = slice(b0, b0 + nb)
+            rs = resid if resid.shape[0] == 1 else resid[sub]
+            eng.loglike(prob, t, diag, hyper[sub], None if ex is None else ex[sub], rs,
+                        out_ll=ll[sub], out_info=info[sub], max_chunk=nb)
+            ws = eng.current_workspace()
+            view = ws[:nb * stride * 8].view(torch.float64).view(nb, stride // ld, ld)
+            L = torch.tril(view[:, :n, :n])
+            rp = rs[:, perm].expand(nb, n) if rs.shape[0] == 1 else rs[:, perm]
+            alpha = torch.cholesky_solve(rp.unsqueeze(2).contiguous(), L)
+            W = torch.cholesky_inverse(L)
+            W.baddbmm_(alpha, alpha.transpose(1, 2), alpha=-1.0)
+            partial = torch.empty(nb * ctas * 24, dtype=torch.float64, device=eng.device)
+            hy = hyper[sub].contiguous()
+            exs = None if ex is None else ex[sub].contiguous()
+            st = eng.lib.mf_grad_contract(eng.handle, ctypes.byref(prob), nb, eng.ptr(t), eng.ptr(hy), eng.ptr(exs),
+                                          eng.ptr(W), n, n * n, eng.ptr(partial),
+                                          ctypes.c_void_p(grad.data_ptr() + b0 * npar * 8), eng.stream())
+            _lib.check(eng.lib, eng.handle, st, "mf_grad_contract")
+            eng.launches += 2
+            del L, W, alpha, partial
+        grad[info != 0] = float("nan")
+        if want_torch:
+            return ll, grad
+        return ll.cpu().numpy(), grad.cpu().numpy()
+
     def _batch_loglike(self, prob, diag_key, diag_make, A, extra, Bm):
         """A: (B, hyper_len) numpy or torch; returns same kind, shape (B,)."""
         eng = self.engine

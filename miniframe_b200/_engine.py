@@ -157,12 +157,19 @@ class Engine(object):
         self.launches += 1
         return z, ll
 
-    def loglike(self, prob, t, diag_add, hyper, extra, resid, out_ll=None, out_info=None):
+    def current_workspace(self):
+        """The workspace buffer of torch's current stream (after loglike: the factors, first chunk first)."""
+        return self._ws[self._stream_id()]
+
+    def loglike(self, prob, t, diag_add, hyper, extra, resid, out_ll=None, out_info=None, max_chunk=None):
         """The whole hot path for a batch held on the device.  Returns (ll, info)."""
         torch = _torch()
         B = hyper.shape[0]
         n = prob.n_series * prob.n_epochs
-        ws, ws_bytes = self.workspace(B, n)
+        ws, ws_bytes = self.workspace(B if max_chunk is None else min(B, max_chunk), n)
+        hyper = hyper.contiguous()
+        if extra is not None:
+            extra = extra.contiguous()
         ll = out_ll if out_ll is not None else torch.empty(B, dtype=torch.float64, device=self.device)
         info = out_info if out_info is not None else torch.empty(B, dtype=torch.int32, device=self.device)
         rs = 0 if (resid is None or resid.shape[0] == 1) else resid.shape[1]

@@ -50,6 +50,9 @@ SIGNATURES = {
                            c_void_p]),
     "mf_solve_logdet": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, c_int64, c_void_p,
                                 c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mf_grad_ctas": (c_int, [c_int]),
+    "mf_grad_contract": (c_int, [c_void_p, POINTER(Problem), c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "mf_probe_fp64": (c_int, [c_void_p, c_int, c_int, POINTER(c_float), POINTER(c_double),
                               c_void_p]),
 }

@@ -114,6 +114,9 @@ extern "C" int mf_set_option(mf_handle_t h, const char* name, int value) {
     } else if (!strcmp(name, "potrf_group")) {
         if (value < 0) MF_FAIL(h, MF_ERR_INVALID, "potrf_group must be >= 0");
         h->opt.potrf_group = value;
+    } else if (!strcmp(name, "potrf_map")) {
+        if (value < 0 || value > 2) MF_FAIL(h, MF_ERR_INVALID, "potrf_map is 0 (choose), 1 or 2");
+        h->opt.potrf_map = value;
     } else if (!strcmp(name, "cov_ctas")) {
         if (value < 0) MF_FAIL(h, MF_ERR_INVALID, "cov_ctas must be >= 0");
         h->opt.cov_ctas = value;

@@ -78,6 +78,7 @@ struct Params {
                           // [3] info of the failure
     unsigned* rowdone;    // per group rd_stride words: block columns finished per 64-row block
     int rd_stride;
+    int map_back;         // tile `it` of block column jb goes to CTA (it - jb) mod G instead of (it + jb) mod G
     int* counter;         // next matrix to hand out (one CTA per matrix, zeroed before the launch)
 };
 
@@ -443,7 +444,13 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
             fence_async_proxy();
 
             if (COOP) publish_pending();      // (the barrier above: the last tile of the previous block column is complete)
-            const int it_first = COOP ? (rank - jb % G + G) % G : 0;
+            // Which CTA takes which tile.  (it + jb) mod G keeps a 64-row block with one CTA for the
+            // whole factorisation - and makes the CTAs that own the last row blocks of a large matrix
+            // do twice the average work (sum of rb^2 over their row blocks).  (it - jb) mod G walks
+            // the row blocks across the CTAs instead: the tiles of the late, long block columns rotate
+            // over all CTAs, and the CTA that owns a diagonal tile has nothing else to do in the block
+            // column before it once there are fewer tiles than CTAs.
+            const int it_first = !COOP ? 0 : (p.map_back ? (rank + jb) % G : (rank - jb % G + G) % G);
             const unsigned seq0 = ordinal * (unsigned)(ncb + 2);      // rowdone = seq0 + finished block columns
             bool have_L = !COOP;
             if (COOP && tid == 0) known[1] = 0;                        // diagonal rows of this block column
@@ -986,6 +993,7 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
     p.sync = nullptr;
     p.rowdone = nullptr;
     p.rd_stride = 0;
+    p.map_back = h->opt.potrf_map == 2 ? 0 : 1;
     p.counter = reinterpret_cast<int*>(h->coop_sync);
     // Tile variant.  Small matrices: 64-row tiles (one 8-row fragment per warp, 80 registers) and
     // THREE CTAs per SM.  The 64 sequential pivots per block column are a latency chain that only

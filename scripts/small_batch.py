@@ -24,15 +24,23 @@ def run(N, B, group=None, reps=3):
     n = 3 * N
     return best, (n ** 3 / 3 + n ** 2) * B / best / 1e9, ll.cpu().numpy(), (t, rv, rhk, bis, e1, e2, e3, H)
 
+from miniframe_b200._engine import Engine
 rows = []
-for N, B in [(200, 1), (500, 1), (500, 8), (500, 64), (500, 148), (2000, 8), (2000, 64)]:
+for N, B in [(200, 1), (200, 9), (500, 1), (500, 8), (500, 64), (500, 148), (2000, 1), (2000, 8), (2000, 64)]:
     ms1, tf1, ll1, _ = run(N, B, group=1)
-    msg, tfg, llg, _ = run(N, B)
-    rows.append({"N": N, "B": B, "one_cta_ms": ms1, "one_cta_tflops": tf1, "coop_ms": msg, "coop_tflops": tfg,
-                 "max_rel_diff": float(np.max(np.abs(llg - ll1) / np.abs(ll1)))})
-    print(json.dumps(rows[-1]), flush=True)
+    row = {"N": N, "B": B, "one_cta_ms": ms1, "one_cta_tflops": tf1}
+    for mp in (1, 2):
+        Engine.get().set_option("potrf_map", mp)
+        msg, tfg, llg, _ = run(N, B)
+        row.update({"coop_ms_map%d" % mp: msg, "coop_tflops_map%d" % mp: tfg,
+                    "bit_identical_map%d" % mp: bool(np.array_equal(llg, ll1))})
+    Engine.get().set_option("potrf_map", 0)
+    rows.append(row)
+    print(json.dumps(row), flush=True)
 if len(sys.argv) > 1 and sys.argv[1] == "big":
     for B in (1, 8):
-        ms, tf, ll, (t, rv, rhk, bis, e1, e2, e3, H) = run(10000, B, reps=2)
-        row = {"N": 10000, "B": B, "coop_ms": ms, "coop_tflops": tf, "ll0": float(ll[0])}
-        print(json.dumps(row), flush=True)
+        for mp in (1, 2):
+            Engine.get().set_option("potrf_map", mp)
+            ms, tf, ll, (t, rv, rhk, bis, e1, e2, e3, H) = run(10000, B, reps=2)
+            row = {"N": 10000, "B": B, "map": mp, "coop_ms": ms, "coop_tflops": tf, "ll0": float(ll[0])}
+            print(json.dumps(row), flush=True)
