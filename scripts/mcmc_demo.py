@@ -11,15 +11,17 @@ from oracle import gp_oracle as go
 
 lo = np.log([5.0, 0.5, 15.0, 1e-3, 0.1, 0.1, 0.1, 0.1, 0.1])
 hi = np.log([100.0, 2.0, 35.0, 0.1, 10.0, 10.0, 1.0, 10.0, 10.0])
-for N, walkers, steps in [(200, 18, 200), (200, 256, 100), (500, 64, 50), (500, 592, 20)]:
+for N, walkers, steps in [(200, 18, 400), (200, 256, 100), (500, 64, 50), (500, 592, 20)]:
     t, (rv, rhk, bis), (e1, e2, e3) = go.synthetic_series(N, seed=1)
     gp = BIGgp(kernels.QuasiPeriodic, [None, None, None], t=t, rv=rv, rverr=e1, rhk=rhk, sig_rhk=e2, bis=bis, sig_bis=e3)
     p0 = np.random.default_rng(2).uniform(lo, hi, size=(walkers, 9))
-    s = EnsembleSampler(walkers, 9, box_log_prob(gp, lo, hi), seed=1, device="cuda")
-    p, lnp, _ = s.run_mcmc(p0, 5)
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    p, lnp, _ = s.run_mcmc(p, steps)
-    torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    print(json.dumps({"N": N, "n": 3 * N, "walkers": walkers, "steps": steps, "steps_per_s": steps / dt,
-                      "evals_per_s": steps * walkers / dt, "acceptance": float(s.acceptance_fraction.mean()),
-                      "best_lnprob": float(lnp.max())}), flush=True)
+    for graph in (True, False):
+        s = EnsembleSampler(walkers, 9, box_log_prob(gp, lo, hi), seed=1, device="cuda", use_graph=graph)
+        p, lnp, _ = s.run_mcmc(p0, 5)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        p, lnp, _ = s.run_mcmc(p, steps)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        print(json.dumps({"N": N, "n": 3 * N, "walkers": walkers, "steps": steps, "cuda_graph": bool(s._graph),
+                          "graph_error": getattr(s, "graph_error", None), "steps_per_s": steps / dt,
+                          "evals_per_s": steps * walkers / dt, "acceptance": float(s.acceptance_fraction.mean()),
+                          "best_lnprob": float(lnp.max())}), flush=True)

@@ -68,11 +68,12 @@ def test_gpu_gradient_against_analytic_oracle(N, kname, jitter):
         worst = max(worst, _close(g[b], wg))
     print("N %d %s jitter %s: worst gradient error %.2e of scale" % (N, kname, jitter, worst))
     assert worst <= GRAD_RTOL
-    # the batch result does not depend on the slot, torch in -> torch out, single call = row 0
+    # torch in -> torch out with the same numbers; the single call is row 0 (the library's
+    # triangular inverse takes another code path for a batch of one: compare to tolerance)
     again = gp.log_likelihood_grad_batch(torch.as_tensor(H, device="cuda"), *(() if not jitter else (None, torch.as_tensor(J, device="cuda"))))
     assert again[1].is_cuda and np.array_equal(again[1].cpu().numpy(), g)
     one = gp.log_likelihood_grad(H[0], [], *(() if not jitter else (J[0],)))
-    assert one[0] == ll[0] and np.array_equal(one[1], g[0])
+    assert one[0] == ll[0] and _close(one[1], g[0]) <= 1e-10
 
 
 @pytest.mark.gpu
