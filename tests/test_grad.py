@@ -73,7 +73,7 @@ def test_gpu_gradient_against_analytic_oracle(N, kname, jitter):
     again = gp.log_likelihood_grad_batch(torch.as_tensor(H, device="cuda"), *(() if not jitter else (None, torch.as_tensor(J, device="cuda"))))
     assert again[1].is_cuda and np.array_equal(again[1].cpu().numpy(), g)
     one = gp.log_likelihood_grad(H[0], [], *(() if not jitter else (J[0],)))
-    assert one[0] == ll[0] and _close(one[1], g[0]) <= 1e-10
+    assert one[0] == ll[0] and _close(one[1], g[0]) <= GRAD_RTOL
 
 
 @pytest.mark.gpu
