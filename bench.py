@@ -324,7 +324,11 @@ def run_ours(args, rank, local_rank, world):
         # power manager has settled - the figure a kernel timed inside a long step can reach
         peaks["dmma_probe_tflops"] = max(eng.probe_fp64(0, 4000) for _ in range(3))
         peaks["dfma_probe_tflops"] = max(eng.probe_fp64(1, 4000) for _ in range(3))
-        peaks["dmma_probe_sustained_tflops"] = eng.probe_fp64(0, 120000)
+        probe_clocks = ClockSampler(local_rank)
+        peaks["dmma_probe_sustained_tflops"] = eng.probe_fp64(0, 400000)     # two launches of ~0.5 s
+        pc = probe_clocks.stop()
+        peaks["dmma_probe_sustained_clocks"] = {"sm_mhz": pc["sm_mhz"], "power_w_max": pc.get("power_w_max"),
+                                                "reasons": pc["reasons"]}
         del a, b
 
     launches = [0]
@@ -416,6 +420,7 @@ def run_ours(args, rank, local_rank, world):
         e2e_parity = float((out_host[rank * B:(rank + 1) * B].to(dev) - ll_d).abs().max().item())
 
     # ---- strong scaling: BASELINE configs[2], a FIXED global batch cut across the ranks ----
+    ws = None                                  # the engine re-sizes its workspace for the larger shards
     strong = None
     if world > 1 and not args.no_strong:
         strong = []

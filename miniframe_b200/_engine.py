@@ -97,9 +97,13 @@ class Engine(object):
             return ws, batch * per                # the cached buffer already holds the whole batch
         cap = self.max_workspace_bytes
         if cap is None:
+            # grow: give the old buffer back first, then size the new one by what is really free
+            # (somebody else may still hold a reference to the old one)
+            self._ws.pop(sid, None)
+            ws = None
+            torch.cuda.empty_cache()
             free, _ = torch.cuda.mem_get_info(self.device)
-            have = 0 if ws is None else ws.numel()
-            cap = int(0.7 * (free + have))
+            cap = int(0.7 * free)
         count = max(1, min(batch, cap // per))
         need = count * per
         if ws is None or ws.numel() < need:

@@ -205,6 +205,13 @@ class EnsembleSampler(object):
                     self._one_step()
                 for k, v in keep.items():
                     st[k].copy_(v)
+                # the graph's kernels hold pointers into the likelihood workspace of this stream:
+                # keep that buffer alive for as long as the graph (the engine may outgrow it)
+                try:
+                    from ._engine import Engine
+                    self._pinned = Engine.get().current_workspace()
+                except Exception:
+                    self._pinned = None
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, stream=side):
                     self._one_step()
