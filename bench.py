@@ -325,6 +325,7 @@ def run_ours(args, rank, local_rank, world):
         peaks["dmma_probe_tflops"] = max(eng.probe_fp64(0, 4000) for _ in range(3))
         peaks["dfma_probe_tflops"] = max(eng.probe_fp64(1, 4000) for _ in range(3))
         probe_clocks = ClockSampler(local_rank)
+        time.sleep(0.4)                                                      # nvidia-smi needs a moment to start
         peaks["dmma_probe_sustained_tflops"] = eng.probe_fp64(0, 400000)     # two launches of ~0.5 s
         pc = probe_clocks.stop()
         peaks["dmma_probe_sustained_clocks"] = {"sm_mhz": pc["sm_mhz"], "power_w_max": pc.get("power_w_max"),

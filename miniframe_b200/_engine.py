@@ -97,20 +97,26 @@ class Engine(object):
             return ws, batch * per                # the cached buffer already holds the whole batch
         cap = self.max_workspace_bytes
         if cap is None:
-            # grow: give the old buffer back first, then size the new one by what is really free
-            # (somebody else may still hold a reference to the old one)
-            self._ws.pop(sid, None)
-            ws = None
-            torch.cuda.empty_cache()
             free, _ = torch.cuda.mem_get_info(self.device)
-            cap = int(0.7 * free)
+            have = 0 if ws is None else ws.numel()
+            cap = int(0.7 * (free + have))
         count = max(1, min(batch, cap // per))
         need = count * per
-        if ws is None or ws.numel() < need:
+        if ws is None or ws.numel() < 0.9 * need:
+            # grow (a cached buffer within 10 % of what memory allows is kept: free memory
+            # fluctuates): give the old buffer back first, then size the new one by what is
+            # really free (somebody else may still hold a reference to the old one)
             self._ws.pop(sid, None)
             ws = None
+            if self.max_workspace_bytes is None:
+                torch.cuda.empty_cache()
+                free, _ = torch.cuda.mem_get_info(self.device)
+                count = max(1, min(batch, int(0.7 * free) // per))
+                need = count * per
             ws = torch.empty(need, dtype=torch.uint8, device=self.device)
             self._ws[sid] = ws
+        else:
+            need = min(need, ws.numel() // per * per)
         return ws, need
 
     def drop_workspaces(self):
