@@ -493,11 +493,12 @@ static int launch_cov_il(mf_handle_t h, const CovParams& p, cudaStream_t st) {
     MF_CUDA_CHECK(h, cudaFuncSetAttribute(mf_cov_build_big_il_kernel<KERNEL>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int by = p.batch < 65535 ? p.batch : 65535;
-    // CTAs per sample: with one dense output stream the number of matrices in flight no longer
-    // matters much (measured, 2368 x n = 1500: 4 / 8 / 17 / 34 / 68 / 136 CTAs per sample ->
-    // 5.32 / 5.37 / 5.29 / 5.13 / 4.75 / 4.09 TB/s): eight, so that a CTA's coefficient set-up
-    // is spread over many tiles, more only when the batch alone cannot fill the GPU
-    int bx = h->opt.cov_ctas > 0 ? h->opt.cov_ctas : 8;
+    // CTAs per sample: about sixteen pair tiles per CTA, so that a CTA's coefficient set-up is
+    // spread over many tiles while every sample still has enough CTAs in flight (measured, n = 1500,
+    // 136 tiles: 4 / 8 / 17 / 34 / 68 / 136 CTAs per sample -> 5.32 / 5.37 / 5.29 / 5.13 / 4.75 /
+    // 4.09 TB/s; n = 6000, 2016 tiles: 8 / 34 / 136 -> 5.04 / 5.21 / 5.51 TB/s); more when the
+    // batch alone cannot fill the GPU
+    int bx = h->opt.cov_ctas > 0 ? h->opt.cov_ctas : (p.n_tiles + 15) / 16;
     if (h->opt.cov_ctas == 0 && (long)bx * by < 3L * h->sm_count) bx = (3 * h->sm_count + by - 1) / by;
     if (bx > p.n_tiles) bx = p.n_tiles;
     mf_cov_build_big_il_kernel<KERNEL><<<dim3(bx, by), THREADS, smem, st>>>(q);
