@@ -101,6 +101,16 @@ class ClockSampler(object):
                                          stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
+        # nvidia-smi needs up to a second before its first sample: wait for it, so that short
+        # regions are not missed
+        t_end = time.time() + 3.0
+        while self.proc is not None and time.time() < t_end:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    break
+            except OSError:
+                pass
+            time.sleep(0.05)
 
     def stop(self):
         if self.proc is None:
@@ -129,6 +139,7 @@ class ClockSampler(object):
                         reasons.add(name)
         os.unlink(self.path)
         return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_mhz_min": min(sm) if sm else None,
                 "sm_max_mhz": max(smax) if smax else None,
                 "power_w_max": max(power) if power else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
@@ -325,11 +336,11 @@ def run_ours(args, rank, local_rank, world):
         peaks["dmma_probe_tflops"] = max(eng.probe_fp64(0, 4000) for _ in range(3))
         peaks["dfma_probe_tflops"] = max(eng.probe_fp64(1, 4000) for _ in range(3))
         probe_clocks = ClockSampler(local_rank)
-        time.sleep(0.4)                                                      # nvidia-smi needs a moment to start
         peaks["dmma_probe_sustained_tflops"] = eng.probe_fp64(0, 400000)     # two launches of ~0.5 s
         pc = probe_clocks.stop()
-        peaks["dmma_probe_sustained_clocks"] = {"sm_mhz": pc["sm_mhz"], "power_w_max": pc.get("power_w_max"),
-                                                "reasons": pc["reasons"]}
+        peaks["dmma_probe_sustained_clocks"] = {"sm_mhz_median": pc["sm_mhz"], "sm_mhz_min": pc.get("sm_mhz_min"),
+                                                "power_w_max": pc.get("power_w_max"), "reasons": pc["reasons"],
+                                                "samples": pc["samples"]}
         del a, b
 
     launches = [0]

@@ -45,7 +45,7 @@ def main():
         table[key] = {"kernel": name, "matrices": args.matrices, "matrix_order": args.order,
                       "dram_bytes_read": val["dram__bytes_read.sum"], "dram_bytes_write": val["dram__bytes_write.sum"],
                       "duration_ms": float(r[ix["gpu__time_duration.sum"]].replace(",", "")) *
-                                     {"msecond": 1.0, "usecond": 1e-3, "second": 1e3, "nsecond": 1e-6}[units[ix["gpu__time_duration.sum"]]],
+                                     {"msecond": 1.0, "ms": 1.0, "usecond": 1e-3, "us": 1e-3, "second": 1e3, "s": 1e3, "nsecond": 1e-6, "ns": 1e-6}[units[ix["gpu__time_duration.sum"]]],
                       "source": src, "source_sha256": hashlib.sha256(open(os.path.join(ROOT, src), "rb").read()).hexdigest(),
                       "capture": args.capture, "raw_export": os.path.relpath(args.csv, ROOT)}
         print(key, json.dumps(table[key])[:300])
