@@ -387,8 +387,10 @@ def run_ours(args, rank, local_rank, world):
 
     for _ in range(args.warmup):
         step()
-    barrier()
+    # (the clock sampler waits for nvidia-smi's first sample: start it BEFORE the barrier, or the
+    # other ranks would spend that second waiting for rank 0 inside their timed all-gather)
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
     events = []
     launches[0] = 0
     ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

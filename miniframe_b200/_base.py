@@ -139,7 +139,7 @@ class GPBase(object):
         for i, m in enumerate(self.means):
             if m is None:
                 continue
-            vals = _means.batch_eval(m, t, Bm[:, k:k + m._parsize])
+            vals = _means.batch_eval(m, t, Bm[:, k:k + m._parsize], t_host=self.t)
             if vals is None:
                 return None
             rows[:, i * N:(i + 1) * N] -= vals

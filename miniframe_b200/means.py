@@ -214,9 +214,10 @@ def _kepler_rv_batch(torch, t, P, K, e, w, T0, iterations):
     return K * (e * torch.cos(w) + torch.cos(w + nu))
 
 
-def batch_eval(mean, t, pars):
+def batch_eval(mean, t, pars, t_host=None):
     """``mean``: an instance of a class of this module; ``t``: (N,) float64 tensor;
-    ``pars``: (B, mean._parsize) tensor on the same device.  Returns the (B, N) tensor of
+    ``pars``: (B, mean._parsize) tensor on the same device; ``t_host``: the same times as a host
+    array when the caller has them (saves a device round trip).  Returns the (B, N) tensor of
     m(t; pars[b]) or None when the class has no batched form."""
     import torch
     cls = type(mean)
@@ -225,7 +226,8 @@ def batch_eval(mean, t, pars):
     if cls is Constant:
         return c[0].expand(-1, t.numel()).clone()
     if cls is Linear:
-        tmean = float(np.asarray(t.detach().cpu()).mean())      # numpy's mean, as the scalar path
+        # numpy's mean, as the scalar path
+        tmean = float(np.asarray(t.detach().cpu() if t_host is None else t_host, dtype=float).mean())
         return c[0] * (tt - tmean) + c[1]
     if cls in (Parabola, Cubic):
         y = torch.zeros((pars.shape[0], t.numel()), dtype=t.dtype, device=t.device)
