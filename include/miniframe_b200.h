@@ -215,6 +215,16 @@ int mf_solve_logdet(mf_handle_t h, int batch, int n,
                     double* z, double* ll, const int32_t* info, void* stream);
 
 /*
+ * Keplerian mean function for a batch of parameter rows, the expensive part of the residual
+ * y - mean(b) (BIGgp.py:303; means.py:143-216: the reference's fixed-count iteration for the
+ * eccentric anomaly, `iterations` = 100, 500 for planet b of TOI175keplerians).
+ *   pars  [batch x 5]  (P, K, e, w, T0) per row (T0 = t[0] - P phi / 2pi for the phase form)
+ *   out   [batch x n_epochs], rows out_stride doubles apart; accumulate != 0 adds to it
+ */
+int mf_kepler_rv(mf_handle_t h, int batch, int n_epochs, const double* t, const double* pars,
+                 int iterations, double* out, int64_t out_stride, int accumulate, void* stream);
+
+/*
  * Gradient of the log-likelihood with respect to the hyper-parameters (not in the
  * reference; the consumer would be an optimiser or HMC on minus_log_likelihood,
  * BIGgp.py:315-317):  grad[b][k] = -1/2 sum_{R,C} W_b[R][C] dK_b[R][C]/dtheta_k  with

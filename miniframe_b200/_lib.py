@@ -50,6 +50,8 @@ SIGNATURES = {
                            c_void_p]),
     "mf_solve_logdet": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, c_int64, c_void_p,
                                 c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mf_kepler_rv": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int,
+                             c_void_p]),
     "mf_grad_ctas": (c_int, [c_int]),
     "mf_grad_contract": (c_int, [c_void_p, POINTER(Problem), c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_int64, c_int64, c_void_p, c_void_p, c_void_p]),

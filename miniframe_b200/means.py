@@ -202,6 +202,20 @@ class TOI175keplerians(MeanModel):
 # numpy ``__call__`` above, so both agree to the last couple of ulp of sin/cos.  Returns None for
 # any other class (user-defined means, Sum): the caller then loops over ``__call__`` on the host.
 def _kepler_rv_batch(torch, t, P, K, e, w, T0, iterations):
+    if t.is_cuda:
+        # one kernel for the whole batch and all iterations (csrc/mf_means.cu)
+        import ctypes
+        from ._engine import Engine
+        eng = Engine.get()
+        B, N = P.shape[0], t.shape[-1]
+        pars = torch.cat([x.expand(B, 1) for x in (P, K, e, w, T0)], dim=1).contiguous()
+        out = torch.empty((B, N), dtype=torch.float64, device=t.device)
+        st = eng.lib.mf_kepler_rv(eng.handle, B, N, eng.ptr(t.reshape(-1).contiguous()), eng.ptr(pars),
+                                  int(iterations), eng.ptr(out), N, 0, eng.stream())
+        if st != 0:
+            raise RuntimeError("mf_kepler_rv failed: %s" % eng.lib.mf_last_error(eng.handle).decode())
+        eng.launches += 1
+        return out
     M = 2 * np.pi * (t - T0) / P
     E0 = M + e * torch.sin(M) + 0.5 * (e ** 2) * torch.sin(2 * M)
     M0 = E0 - e * torch.sin(E0)

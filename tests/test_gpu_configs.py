@@ -216,3 +216,23 @@ def test_config5_one_large_matrix_cooperative(mf):
     from miniframe_b200._engine import Engine
     Engine.get().drop_workspaces()
     torch.cuda.empty_cache()
+
+
+def test_keplerian_means_on_the_device(mf):
+    """means.batch_eval on device tensors runs the Keplerian classes through mf_kepler_rv (one kernel
+    for the whole batch and the reference's 100 / 500 fixed-point iterations, means.py:143-216):
+    against each class's own numpy __call__."""
+    import torch
+    from miniframe_b200 import means
+    rng = np.random.default_rng(4)
+    t = np.sort(rng.uniform(0.0, 80.0, 257))
+    td = torch.as_tensor(t, device="cuda")
+    cases = {means.oldKeplerian: lambda: [rng.uniform(5, 40), rng.uniform(1, 10), rng.uniform(0, 0.6), rng.uniform(0, 6), rng.uniform(0, 30)],
+             means.Keplerian: lambda: [rng.uniform(5, 40), rng.uniform(1, 10), rng.uniform(0, 0.6), rng.uniform(0, 6), rng.uniform(0, 6), rng.normal()],
+             means.TOI175keplerians: lambda: [v for _ in range(3) for v in (rng.uniform(2, 40), rng.uniform(1, 5), rng.uniform(0, 0.4), rng.uniform(0, 6), rng.uniform(0, 6))] + [rng.normal()]}
+    for cls, draw in cases.items():
+        P = np.array([draw() for _ in range(7)])
+        got = means.batch_eval(cls.initialize(), td, torch.as_tensor(P, device="cuda"), t_host=t)
+        assert got.is_cuda and tuple(got.shape) == (7, t.size)
+        want = np.array([cls(*row)(t) for row in P])
+        assert np.abs(got.cpu().numpy() - want).max() <= 1e-11 * max(1.0, np.abs(want).max()), cls.__name__
