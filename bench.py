@@ -330,13 +330,16 @@ def run_ours(args, rank, local_rank, world):
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1_))
         peaks["cublas_dgemm_4096_tflops"] = 2 * 4096 ** 3 / (best * 1e-3) / 1e12
-        # burst: ~5 ms launches, best of three (the pipe's rate); sustained: the same register
-        # probe run for as long as one factorisation launch of this bench (~150 ms), where the
-        # power manager has settled - the figure a kernel timed inside a long step can reach
+        # the register-resident DMMA probe (mma.sync.m8n8k4.f64, 16 independent accumulator tiles per
+        # warp): ~5 ms bursts at 32 warps per SM, and ~0.5 s launches at 16 warps per SM - the
+        # occupancy of the factorisation kernel - with clocks and power sampled during them.  (At
+        # 32 warps per SM the probe itself falls to 29.7 TFLOP/s after ~10 ms; at 16 it holds the
+        # full rate for seconds at ~430 W: profiles/r2_fp64_probes.txt.  The pipe's sustained peak is
+        # the burst peak.)
         peaks["dmma_probe_tflops"] = max(eng.probe_fp64(0, 4000) for _ in range(3))
         peaks["dfma_probe_tflops"] = max(eng.probe_fp64(1, 4000) for _ in range(3))
         probe_clocks = ClockSampler(local_rank)
-        peaks["dmma_probe_sustained_tflops"] = eng.probe_fp64(0, 400000)     # two launches of ~0.5 s
+        peaks["dmma_probe_sustained_tflops"] = eng.probe_fp64(30, 400000)    # two launches of ~0.45 s
         pc = probe_clocks.stop()
         peaks["dmma_probe_sustained_clocks"] = {"sm_mhz_median": pc["sm_mhz"], "sm_mhz_min": pc.get("sm_mhz_min"),
                                                 "power_w_max": pc.get("power_w_max"), "reasons": pc["reasons"],
@@ -504,8 +507,8 @@ def run_ours(args, rank, local_rank, world):
     per_launch = min(chunk, B)
     potrf_tflops = flops_per_eval(n) * per_launch / (potrf_ms * 1e-3) / 1e12
     build_gbs = build_bytes_per_eval(n) * per_launch / (build_ms * 1e-3) / 1e9
-    fp64_peak = max(peaks.get("cublas_dgemm_4096_tflops", 0.0), peaks.get("dmma_probe_tflops", 0.0))
-    fp64_sustained = peaks.get("dmma_probe_sustained_tflops", 0.0)
+    fp64_peak = max(peaks.get("cublas_dgemm_4096_tflops", 0.0), peaks.get("dmma_probe_tflops", 0.0),
+                    peaks.get("dmma_probe_sustained_tflops", 0.0))
     potrf_traffic, potrf_note = ncu_traffic("mf_potrf_ll_kernel", n, per_launch)
     build_traffic, build_note = ncu_traffic("mf_cov_build_big_il_kernel", n, per_launch)
     line = {
@@ -522,13 +525,10 @@ def run_ours(args, rank, local_rank, world):
         "gpu_launches": gpu_launches,
         "roofline": {"kernel": "mf_potrf_ll_kernel", "bound": "tensor", "achieved": potrf_tflops,
                      "peak": fp64_peak, "unit": "TFLOP/s", "frac": potrf_tflops / fp64_peak,
-                     "peak_sustained": fp64_sustained,
-                     "frac_of_sustained": potrf_tflops / fp64_sustained if fp64_sustained else None,
                      "traffic": potrf_traffic, "traffic_unit": potrf_note,
-                     "peak_source": "FP64 is not in MEASURED_PEAKS.json: `peak` = max of cuBLAS DGEMM 4096^3 "
-                                    "(best of 5) and the DMMA register probe in ~5 ms bursts, `peak_sustained` = "
-                                    "the same probe run for the duration of one factorisation launch; all "
-                                    "measured in this run",
+                     "peak_source": "FP64 is not in MEASURED_PEAKS.json: max of cuBLAS DGEMM 4096^3 (best of 5) and "
+                                    "the DMMA register probe (5 ms bursts, and 0.45 s launches at the "
+                                    "factorisation's occupancy), all measured in this run",
                      "ms_per_launch": potrf_ms, "evals_per_launch": per_launch,
                      "flops_per_eval": flops_per_eval(n)},
         "roofline_build": {"kernel": "mf_cov_build_big_il_kernel", "bound": "hbm", "achieved": build_gbs,

@@ -10,5 +10,5 @@ echo "== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -q --tb=short -
 echo "== bench"; timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/ab_bench.json 2> gpurun_out/ab_bench.err; echo "rc=$?"; tail -3 gpurun_out/ab_bench.err; python - <<'PY'
 import json
 d=json.load(open('gpurun_out/ab_bench.json'))
-print("value %.0f e2e %.0f | potrf %.2f TF/s frac %.3f (sust %.3f) ms %.2f | build %.0f GB/s frac %.3f ms %.2f | peaks %s | clocks %s | cpu %s" % (d['value'], d['e2e']['value'], d['roofline']['achieved'], d['roofline']['frac'], d['roofline']['frac_of_sustained'] or 0, d['roofline']['ms_per_launch'], d['roofline_build']['achieved'], d['roofline_build']['frac'], d['roofline_build']['ms_per_launch'], d['fp64_peaks_measured'], d['clocks'], d['cpu_baseline']))
+print("value %.0f e2e %.0f | potrf %.2f TF/s frac %.3f ms %.2f | build %.0f GB/s frac %.3f ms %.2f | peaks %s | clocks %s | cpu %s" % (d['value'], d['e2e']['value'], d['roofline']['achieved'], d['roofline']['frac'], d['roofline']['ms_per_launch'], d['roofline_build']['achieved'], d['roofline_build']['frac'], d['roofline_build']['ms_per_launch'], d['fp64_peaks_measured'], d['clocks'], d['cpu_baseline']))
 PY
