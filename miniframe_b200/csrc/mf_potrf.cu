@@ -115,6 +115,31 @@ __device__ __forceinline__ void tma_box(uint32_t dst, const CUtensorMap* tm, int
         ::"r"(dst), "l"(tm), "r"(c0), "r"(0), "r"(0), "r"(blk8), "r"(mat), "r"(bar), "l"(policy)
         : "memory");
 }
+// One chunk of the ring - expect_tx and the three boxes - issued by ONE elected lane of a fully
+// active warp whose operands are warp-uniform: no divergent branch around it, so the instructions
+// can be scheduled between the tensor-core instructions of the warp that issues them.
+__device__ __forceinline__ void tma_chunk_elect(uint32_t dst, const CUtensorMap* tm, int c0, int blkA, int blkB,
+                                                int mat, uint32_t bar, uint32_t bytes, int two_a) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 pf, pl;\n\t.reg .b32 d2, d3, b2;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "setp.ne.and.b32 q, %8, 0, p;\n\t"
+        "createpolicy.fractional.L2::evict_first.b64 pf, 1.0;\n\t"
+        "createpolicy.fractional.L2::evict_last.b64 pl, 1.0;\n\t"
+        "add.u32 d2, %0, 8192;\n\t"
+        "add.s32 b2, %3, 8;\n\t"
+        "selp.u32 d3, 16384, 8192, q;\n\t"
+        "add.u32 d3, %0, d3;\n\t"
+        "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%6], %7;\n\t"
+        "@p cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%2, 0, 0, %3, %5}], [%6], pf;\n\t"
+        "@q cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[d2], [%1, {%2, 0, 0, b2, %5}], [%6], pf;\n\t"
+        "@p cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[d3], [%1, {%2, 0, 0, %4, %5}], [%6], pl;\n\t}"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(blkA), "r"(blkB), "r"(mat), "r"(bar), "r"(bytes), "r"(two_a)
+        : "memory");
+}
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -135,6 +160,17 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
 }
 __device__ __forceinline__ void fence_async_proxy() {
     asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+// lane 0 adds one to a shared-memory counter without a branch; the old value is looked at later
+__device__ __forceinline__ void atoms_inc_lane0(unsigned& old, uint32_t addr, int lane) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.eq.s32 p, %2, 0;\n\t"
+        "@p atom.shared.add.u32 %0, [%1], 1;\n\t}"
+        : "+r"(old)
+        : "r"(addr), "r"(lane)
+        : "memory");
 }
 
 // MINUS the inverses of the eight diagonal 8 x 8 blocks of L_jj (in Ld), the operand of the row
@@ -205,27 +241,35 @@ __device__ __forceinline__ void potf2_panels(const double* Aw, double* Ld, doubl
     }
     dg0 = live0 ? flip(dg0) : (8 * warp + g == c0 ? 1.0 : 0.0);
     dg1 = live1 ? flip(dg1) : (8 * warp + g == c0 + 1 ? 1.0 : 0.0);
+    // Eight pivots, one dependent chain: broadcast of the pivot, rsqrt, scale, broadcast of the
+    // column, fma.  Nothing else may sit on it: the LAPACK pivot test (d > 0) is only recorded - a
+    // failed pivot poisons what follows with NaNs that nobody uses - and looked at after the
+    // eighth pivot, and lane c keeps 1 / L_cc in a register until then (a store from inside the
+    // chain made the compiler evaluate rsqrt twice per pivot, once for lane 0 alone).
+    int bad = 0;
+    double myrs = 0.0;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        if (dead) break;
         const double d = __shfl_sync(FULL, (c & 1) ? dg1 : dg0, 4 * c + (c >> 1));
-        if (!DBG && !(d > 0.0)) {           // LAPACK dpotrf pivot test
-            if (lane == 0) *failword = j0 + 8 * warp + c + 1;
-            dead = true;
-            break;
-        }
+        if (!DBG && bad == 0 && !(d > 0.0)) bad = c + 1;
         const double rs = rsqrt(d);
-        if (lane == 0) rsbuf[8 * warp + c] = rs;
+        if (lane == c) myrs = rs;
         double& col = (c & 1) ? dg1 : dg0;
         if (t == (c >> 1)) col = (g > c) ? col * rs : (g == c ? d * rs : 0.0);
         if (c < 7) {
-            // column c at rows 2t, 2t + 1 (the columns this lane updates) and at this lane's row
             const double l0 = __shfl_sync(FULL, col, 8 * t + (c >> 1));
             const double l1 = __shfl_sync(FULL, col, 8 * t + 4 + (c >> 1));
             const double lr = __shfl_sync(FULL, col, 4 * g + (c >> 1));
             if (2 * t > c && live0) dg0 = fma(-lr, l0, dg0);
             if (2 * t + 1 > c && live1) dg1 = fma(-lr, l1, dg1);
         }
+    }
+    if (dead) {
+    } else if (bad) {
+        if (lane == 0) *failword = j0 + 8 * warp + bad;
+        dead = true;
+    } else if (lane < 8) {
+        rsbuf[8 * warp + lane] = myrs;
     }
     if (!dead) {
         if (2 * t > g) dg0 = 0.0;           // upper part of the diagonal 8 x 8 block
@@ -285,6 +329,8 @@ __device__ __forceinline__ void potf2_panels(const double* Aw, double* Ld, doubl
 }
 
 // DBG (timing experiments, compiled only with -DMF_EXPERIMENTS; results are garbage): bit mask,
+//   1024 = no ring traffic (no TMA loads, no waits: the loop reads whatever the stages hold),
+//   4096 = TMA loads issued as usual but nobody waits for them,
 //   8 = consume the ring without computing, 32 = skip the diagonal-block factorisation,
 //   64 = skip the triangular solve, 128 = do not load the K tiles, 256 = stream the operands
 //   of every matrix from the first four (L2-resident), 512 = do not store the rows of L
@@ -311,9 +357,12 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
     constexpr int OFF_DINV = OFF_LD + SZ_LD;
     constexpr int OFF_COL = OFF_DINV + SZ_DINV;
     constexpr int OFF_RED = OFF_COL + SZ_COL;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // 128B-swizzled TMA boxes need 1 KB alignment: align by hand, one spare KB is allocated
-    unsigned char* const smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    // 128B-swizzled TMA boxes need 1 KB alignment.  Declared, not computed: the kernel has no static
+    // shared memory, so the array sits at a link-time constant offset of the shared window and every
+    // shared-memory address below folds into an immediate (aligning a generic pointer by hand made
+    // ptxas rebuild the window base - S2R SR_CgaCtaId and a dozen integer instructions - per chunk).
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* const smem = smem_raw;
     double* const Aw = reinterpret_cast<double*>(smem);                 // aliases the stages
     double* const Ld = reinterpret_cast<double*>(smem + OFF_LD);
     double* const Dinv = reinterpret_cast<double*>(smem + OFF_DINV);
@@ -346,7 +395,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
     // Chunks are numbered over the whole kernel lifetime: chunk c lives in stage c % NSTAGE and
     // is that stage's (c / NSTAGE)-th use (use_s, use_k: the next chunk this warp consumes).
     const uint32_t bar_full = smem_u32(smem + OFF_RED + 256);
-    int* const released = reinterpret_cast<int*>(smem + OFF_RED + 256 + 8 * NSTAGE);
+    int* const released = reinterpret_cast<int*>(smem + OFF_RED + 416);
     if (tid == 0) {
         for (int s0 = 0; s0 < NSTAGE; ++s0) {
             mbar_init(bar_full + 8 * s0, 1);
@@ -405,6 +454,9 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
             if (tid == 0) *next_mat = atomicAdd(p.counter, 1);
             __syncthreads();
             mat = *next_mat;
+            // the same value in every lane - and ptxas knows it (a warp reduction lands in a uniform
+            // register), so the TMA coordinates below stay on the uniform datapath
+            mat = __reduce_max_sync(0xffffffffu, mat);
         }
         if (mat >= p.batch) break;
         double* const Kb = p.K + (size_t)mat * p.stride;
@@ -517,6 +569,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                             fenced = have;
                         }
                     }
+                    if (DBG & 1024) return;          // timing experiment: no ring traffic at all
                     mbar_expect_tx(bar, STAGE_BYTES);
                     const int lmat = (DBG & 256) ? (mat & 3) : mat;
                     // the rows of the tile are streamed once, the block column's own rows are read
@@ -530,6 +583,28 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 // else of the next tile of the block column (not from the diagonal tile, whose
                 // factorisation scratch aliases the stages).  Nobody ever waits for a free stage.
                 auto release_stage = [&](int kc) {
+                    if (!COOP) {
+                        // lane 0 counts the warp out (predicated, no branch); the old value reaches
+                        // every lane through a warp reduction, so the "last one out" test and the
+                        // refill are warp-uniform code
+                        __syncwarp();
+                        unsigned old = 0;
+                        atoms_inc_lane0(old, smem_u32(released) + 4 * use_s, lane);
+                        old = __reduce_max_sync(0xffffffffu, old);
+                        if ((old & 7) == 7) {
+                            int tk = kc + NSTAGE, r0 = i0;
+                            bool go = true;
+                            if (tk >= nk) {
+                                tk -= nk;
+                                r0 = i0 + TM;
+                                go = (it > 0) && (it + 1 < ntile);
+                            }
+                            if (go && !(DBG & 1024))
+                                tma_chunk_elect(stage_u32 + use_s * STAGE_BYTES, &p.tmap, tk * KC, r0 >> 3, j0 >> 3,
+                                                (DBG & 256) ? (mat & 3) : mat, bar_full + 8 * use_s, STAGE_BYTES, NMI == 2);
+                        }
+                        return;
+                    }
                     __syncwarp();
                     if (lane == 0) {
                         const int old = atomicAdd(released + use_s, 1);
@@ -613,12 +688,12 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                         if (++use_s == NSTAGE) { use_s = 0; ++use_k; }
                         continue;
                     }
-                    mbar_wait(bar_full + 8 * use_s, use_k & 1);      // chunk kc has landed
+                    if (!(DBG & (1024 | 4096))) mbar_wait(bar_full + 8 * use_s, use_k & 1);      // chunk kc has landed
                     const unsigned char* sb = smem + use_s * STAGE_BYTES;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const int choff = ((4 * h + t) ^ gp) << 4;
                         double2 a[2];
+                        const int choff = ((4 * h + t) ^ gp) << 4;
 #pragma unroll
                         for (int mi = 0; mi < NMI; ++mi)
                             a[mi] = *reinterpret_cast<const double2*>(sb + (8 * tbw + 64 * mi + gp) * 128 + choff);
@@ -1071,31 +1146,60 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
         MF_CUDA_CHECK(h, cudaGetLastError());
         return MF_OK;
     }
-#define MF_LAUNCH(DBG_)                                                                            \
+#define MF_LAUNCH_S(DBG_, GRID_, SMEM_)                                                            \
     do {                                                                                           \
         MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<3, 2, DBG_, 0, 2>,               \
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                                              pf::smem_bytes(3)));                                 \
-        pf::mf_potrf_ll_kernel<3, 2, DBG_, 0, 2><<<grid, pf::THREADS, pf::smem_bytes(3), st>>>(p);    \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_)); \
+        pf::mf_potrf_ll_kernel<3, 2, DBG_, 0, 2><<<GRID_, pf::THREADS, SMEM_, st>>>(p);               \
     } while (0)
+#define MF_LAUNCH(DBG_) MF_LAUNCH_S(DBG_, grid, pf::smem_bytes(3))
 #ifdef MF_EXPERIMENTS
-    // timing-experiment instantiations (scripts/ablate.py); their results are not likelihoods
-    switch (experiment) {
-        case 0: MF_LAUNCH(0); break;
-        case 8: MF_LAUNCH(8); break;
-        case 32: MF_LAUNCH(32); break;
-        case 64: MF_LAUNCH(64); break;
-        case 96: MF_LAUNCH(96); break;
-        case 128: MF_LAUNCH(128); break;
-        case 224: MF_LAUNCH(224); break;
-        case 256: MF_LAUNCH(256); break;
-        case 736: MF_LAUNCH(736); break;
-        default: MF_FAIL(h, MF_ERR_INVALID, "unknown experiment %d", experiment);
+    // timing-experiment instantiations (scripts/ab_kernels.py); their results are not likelihoods.
+    // Bit 2048 on top of any code: ONE CTA per SM (a shared-memory request above half an SM keeps
+    // the second one off).
+    {
+        if (experiment & 8192) {
+            // ... and a ring of FOUR stages instead of three (needs the whole SM's shared memory)
+            const int g1 = batch < h->sm_count ? batch : h->sm_count;
+            const int code = experiment & ~(2048 | 8192);
+#define MF_LAUNCH_6(DBG_)                                                                                       \
+    do {                                                                                                        \
+        MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<4, 1, DBG_, 0, 2>,                          \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, pf::smem_bytes(4))); \
+        pf::mf_potrf_ll_kernel<4, 1, DBG_, 0, 2><<<g1, pf::THREADS, pf::smem_bytes(4), st>>>(p);                 \
+    } while (0)
+            if (code == 0) MF_LAUNCH_6(0);
+            else if (code == 96) MF_LAUNCH_6(96);
+            else if (code == 8) MF_LAUNCH_6(8);
+            else MF_FAIL(h, MF_ERR_INVALID, "unknown experiment %d", experiment);
+#undef MF_LAUNCH_6
+            MF_CUDA_CHECK(h, cudaGetLastError());
+            return MF_OK;
+        }
+        const bool alone = (experiment & 2048) != 0;
+        const int xgrid = alone ? (batch < h->sm_count ? batch : h->sm_count) : grid;
+        const int xsmem = alone ? 120 * 1024 : pf::smem_bytes(3);
+        switch (experiment & ~2048) {
+            case 0: MF_LAUNCH_S(0, xgrid, xsmem); break;
+            case 8: MF_LAUNCH_S(8, xgrid, xsmem); break;
+            case 32: MF_LAUNCH_S(32, xgrid, xsmem); break;
+            case 64: MF_LAUNCH_S(64, xgrid, xsmem); break;
+            case 96: MF_LAUNCH_S(96, xgrid, xsmem); break;
+            case 128: MF_LAUNCH_S(128, xgrid, xsmem); break;
+            case 224: MF_LAUNCH_S(224, xgrid, xsmem); break;
+            case 256: MF_LAUNCH_S(256, xgrid, xsmem); break;
+            case 352: MF_LAUNCH_S(352, xgrid, xsmem); break;
+            case 736: MF_LAUNCH_S(736, xgrid, xsmem); break;
+            case 1760: MF_LAUNCH_S(1760, xgrid, xsmem); break;
+            case 4832: MF_LAUNCH_S(4832, xgrid, xsmem); break;
+            default: MF_FAIL(h, MF_ERR_INVALID, "unknown experiment %d", experiment);
+        }
     }
 #else
     MF_LAUNCH(0);
 #endif
 #undef MF_LAUNCH
+#undef MF_LAUNCH_S
     MF_CUDA_CHECK(h, cudaGetLastError());
     return MF_OK;
 }
