@@ -62,6 +62,8 @@ struct Params {
     // 5-D tensor map over the chunk of matrices for the TMA-fed ring:
     // {column, row 0/2/4/6 of an 8-row group, row parity, 8-row group, matrix}
     alignas(64) CUtensorMap tmap;
+    // the same view with boxes of 128 rows: the row tile of the 128-row kernel in ONE TMA instruction
+    alignas(64) CUtensorMap tmap128;
     int batch;
     int n;
     double* K;
@@ -118,26 +120,21 @@ __device__ __forceinline__ void tma_box(uint32_t dst, const CUtensorMap* tm, int
 // One chunk of the ring - expect_tx and the three boxes - issued by ONE elected lane of a fully
 // active warp whose operands are warp-uniform: no divergent branch around it, so the instructions
 // can be scheduled between the tensor-core instructions of the warp that issues them.
-__device__ __forceinline__ void tma_chunk_elect(uint32_t dst, const CUtensorMap* tm, int c0, int blkA, int blkB,
-                                                int mat, uint32_t bar, uint32_t bytes, int two_a) {
+__device__ __forceinline__ void tma_chunk_elect(uint32_t dst, const CUtensorMap* tmA, const CUtensorMap* tmB, int c0,
+                                                int blkA, int blkB, int mat, uint32_t bar, uint32_t bytes,
+                                                uint32_t b_off) {
     asm volatile(
-        "{\n\t.reg .pred p, q;\n\t.reg .b64 pf, pl;\n\t.reg .b32 d2, d3, b2;\n\t"
+        "{\n\t.reg .pred p;\n\t.reg .b64 pf, pl;\n\t.reg .b32 d3;\n\t"
         "elect.sync _|p, 0xffffffff;\n\t"
-        "setp.ne.and.b32 q, %8, 0, p;\n\t"
         "createpolicy.fractional.L2::evict_first.b64 pf, 1.0;\n\t"
         "createpolicy.fractional.L2::evict_last.b64 pl, 1.0;\n\t"
-        "add.u32 d2, %0, 8192;\n\t"
-        "add.s32 b2, %3, 8;\n\t"
-        "selp.u32 d3, 16384, 8192, q;\n\t"
-        "add.u32 d3, %0, d3;\n\t"
+        "add.u32 d3, %0, %9;\n\t"
         "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%6], %7;\n\t"
         "@p cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
         "[%0], [%1, {%2, 0, 0, %3, %5}], [%6], pf;\n\t"
-        "@q cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
-        "[d2], [%1, {%2, 0, 0, b2, %5}], [%6], pf;\n\t"
         "@p cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
-        "[d3], [%1, {%2, 0, 0, %4, %5}], [%6], pl;\n\t}"
-        ::"r"(dst), "l"(tm), "r"(c0), "r"(blkA), "r"(blkB), "r"(mat), "r"(bar), "r"(bytes), "r"(two_a)
+        "[d3], [%8, {%2, 0, 0, %4, %5}], [%6], pl;\n\t}"
+        ::"r"(dst), "l"(tmA), "r"(c0), "r"(blkA), "r"(blkB), "r"(mat), "r"(bar), "r"(bytes), "l"(tmB), "r"(b_off)
         : "memory");
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
@@ -600,8 +597,9 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                                 go = (it > 0) && (it + 1 < ntile);
                             }
                             if (go && !(DBG & 1024))
-                                tma_chunk_elect(stage_u32 + use_s * STAGE_BYTES, &p.tmap, tk * KC, r0 >> 3, j0 >> 3,
-                                                (DBG & 256) ? (mat & 3) : mat, bar_full + 8 * use_s, STAGE_BYTES, NMI == 2);
+                                tma_chunk_elect(stage_u32 + use_s * STAGE_BYTES, NMI == 2 ? &p.tmap128 : &p.tmap, &p.tmap,
+                                                tk * KC, r0 >> 3, j0 >> 3, (DBG & 256) ? (mat & 3) : mat,
+                                                bar_full + 8 * use_s, STAGE_BYTES, 8192 * NMI);
                         }
                         return;
                     }
@@ -1050,6 +1048,25 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
             tm = &slot->map;
         }
         p.tmap = *tm;
+        mf_tmap_key key2 = {3, K, ld, stride, n, batch};
+        slot = nullptr;
+        const CUtensorMap* tm2 = mf_tmap_find(h, key2, &slot);
+        if (!tm2) {
+            mf_tmap_encode_fn encode = mf_tmap_encoder(h);
+            if (!encode) return MF_ERR_CUDA;
+            const cuuint64_t gdim[5] = {(cuuint64_t)ld, 4, 2, (cuuint64_t)(mf_rows_of(n) / 8), (cuuint64_t)batch};
+            const cuuint64_t gstr[4] = {(cuuint64_t)(2 * ld * 8), (cuuint64_t)(ld * 8), (cuuint64_t)(8 * ld * 8),
+                                        (cuuint64_t)(stride * 8)};
+            const cuuint32_t box[5] = {16, 4, 2, 16, 1};
+            const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+            CUresult cr = encode(&slot->map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, K, gdim, gstr, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr != CUDA_SUCCESS) MF_FAIL(h, MF_ERR_CUDA, "cuTensorMapEncodeTiled (128-row boxes) failed with %d", (int)cr);
+            slot->key.kind = key2.kind;
+            tm2 = &slot->map;
+        }
+        p.tmap128 = *tm2;
     }
     p.batch = batch;
     p.n = n;

@@ -23,6 +23,7 @@ ap.add_argument("--exp", default="0")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--cov", action="store_true")
 ap.add_argument("--tile", type=int, default=0)
+ap.add_argument("--opt", action="append", default=[], help="name=value for mf_set_option")
 args = ap.parse_args()
 
 from miniframe_b200 import _lib
@@ -77,6 +78,9 @@ def timed(fn, reps):
 
 if args.tile:
     eng.set_option("potrf_tile", args.tile)
+for kv in args.opt:
+    k, v = kv.split("=")
+    eng.set_option(k, int(v))
 build(2); potrf(); torch.cuda.synchronize()
 ref = ll.clone()
 print("lib %s  n %d  batch %d  finite %d/%d" % (args.lib, n, B, int(torch.isfinite(ref).sum()), B), flush=True)
