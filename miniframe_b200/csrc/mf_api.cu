@@ -117,6 +117,9 @@ extern "C" int mf_set_option(mf_handle_t h, const char* name, int value) {
     } else if (!strcmp(name, "potrf_map")) {
         if (value < 0 || value > 2) MF_FAIL(h, MF_ERR_INVALID, "potrf_map is 0 (choose), 1 or 2");
         h->opt.potrf_map = value;
+    } else if (!strcmp(name, "potrf_lookahead")) {
+        if (value < 0 || value > 2) MF_FAIL(h, MF_ERR_INVALID, "potrf_lookahead is 0 (choose), 1 (off) or 2 (on)");
+        h->opt.potrf_lookahead = value;
     } else if (!strcmp(name, "cov_ctas")) {
         if (value < 0) MF_FAIL(h, MF_ERR_INVALID, "cov_ctas must be >= 0");
         h->opt.cov_ctas = value;

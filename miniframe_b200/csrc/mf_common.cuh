@@ -28,6 +28,7 @@ struct mf_options {
     int potrf_tile;           // 0 = choose, 1 = 64-row tiles, 2 = 128-row tiles
     int potrf_group;          // 0 = choose, 1 = one CTA per matrix, G > 1 = G CTAs per matrix
     int potrf_map;            // 0 / 1 = tiles walk the CTAs backwards (it - jb), 2 = row blocks stay with a CTA
+    int potrf_lookahead;      // 0 = choose, 1 = plain one-CTA-per-matrix kernel, 2 = look-ahead kernel
     int cov_ctas;             // 0 = choose, else CTAs per sample of the covariance build
     int experiment;           // timing-experiment variant (only with -DMF_EXPERIMENTS builds)
 };

@@ -325,6 +325,116 @@ __device__ __forceinline__ void potf2_panels(const double* Aw, double* Ld, doubl
     if (lane == 0) mbar_arrive(pbar + 8 * warp);       // panel `warp` is in Ld (or the block failed)
 }
 
+// lane 0 adds `inc` to a shared-memory counter without a branch; the old value is looked at later
+__device__ __forceinline__ void atoms_add_lane0(unsigned& old, uint32_t addr, unsigned inc, int lane) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.eq.s32 p, %3, 0;\n\t"
+        "@p atom.shared.add.u32 %0, [%1], %2;\n\t}"
+        : "+r"(old)
+        : "r"(addr), "r"(inc), "r"(lane)
+        : "memory");
+}
+// The whole 64 x 64 diagonal block by ONE warp, in place in Ld (8 x 8 blocks holding MINUS C on
+// entry, L_jj on exit) - potf2_panels with the warp index replaced by a loop over the panels and
+// the mbarriers by __syncwarp; the same operations on the same values in the same order.
+// Returns 0 or the 1-based global index of the first non-positive pivot.
+template <int DBG>
+__device__ __forceinline__ int potf2_one_warp(double* Ld, double* Dinv, double* rsbuf, int nv, int j0) {
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const unsigned FULL = 0xffffffffu;
+    if (DBG & 32) return 0;
+#pragma unroll 1
+    for (int pn = 0; pn < 8; ++pn) {
+        const int c0 = 8 * pn + 2 * t;
+        const bool live0 = c0 < nv, live1 = c0 + 1 < nv;
+        double2 v = *reinterpret_cast<const double2*>(Ld + ldblk(pn, pn) + g * 8 + 2 * t);
+        double dg0 = v.x, dg1 = v.y;
+        for (int q = 0; q < pn; ++q) {
+            const double2 bq = *reinterpret_cast<const double2*>(Ld + ldblk(pn, q) + g * 8 + 2 * t);
+            dmma884(dg0, dg1, bq.x, bq.x);
+            dmma884(dg0, dg1, bq.y, bq.y);
+        }
+        dg0 = live0 ? flip(dg0) : (8 * pn + g == c0 ? 1.0 : 0.0);
+        dg1 = live1 ? flip(dg1) : (8 * pn + g == c0 + 1 ? 1.0 : 0.0);
+        int bad = 0;
+        double myrs = 0.0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const double d = __shfl_sync(FULL, (c & 1) ? dg1 : dg0, 4 * c + (c >> 1));
+            if (bad == 0 && !(d > 0.0)) bad = c + 1;           // LAPACK dpotrf pivot test
+            const double rs = rsqrt(d);
+            if (lane == c) myrs = rs;
+            double& col = (c & 1) ? dg1 : dg0;
+            if (t == (c >> 1)) col = (g > c) ? col * rs : (g == c ? d * rs : 0.0);
+            if (c < 7) {
+                const double l0 = __shfl_sync(FULL, col, 8 * t + (c >> 1));
+                const double l1 = __shfl_sync(FULL, col, 8 * t + 4 + (c >> 1));
+                const double lr = __shfl_sync(FULL, col, 4 * g + (c >> 1));
+                if (2 * t > c && live0) dg0 = fma(-lr, l0, dg0);
+                if (2 * t + 1 > c && live1) dg1 = fma(-lr, l1, dg1);
+            }
+        }
+        if (bad) return j0 + 8 * pn + bad;
+        if (lane < 8) rsbuf[8 * pn + lane] = myrs;
+        if (2 * t > g) dg0 = 0.0;           // upper part of the diagonal 8 x 8 block
+        if (2 * t + 1 > g) dg1 = 0.0;
+        *reinterpret_cast<double2*>(Ld + ldblk(pn, pn) + g * 8 + 2 * t) = make_double2(dg0, dg1);
+        __syncwarp();
+        if (lane < 8) {
+            // column `lane` of MINUS the inverse of the diagonal block (1 / L_ii is the pivot's rsqrt)
+            const double* Lb = Ld + ldblk(pn, pn);
+            double x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                double sum = (i == lane) ? -1.0 : 0.0;
+#pragma unroll
+                for (int k = 0; k < i; ++k) sum -= Lb[i * 8 + k] * x[k];
+                x[i] = sum * rsbuf[8 * pn + i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) Dinv[pn * 64 + i * 8 + lane] = x[i];
+        }
+        __syncwarp();
+        const double2 dv = *reinterpret_cast<const double2*>(Dinv + pn * 64 + g * 8 + 2 * t);
+        for (int bi = pn + 1; bi < 8; bi += 2) {
+            const bool two = bi + 1 < 8;
+            const double2 va = *reinterpret_cast<const double2*>(Ld + ldblk(bi, pn) + g * 8 + 2 * t);
+            double a0 = va.x, a1 = va.y, b0 = 0.0, b1 = 0.0;
+            if (two) {
+                const double2 vb = *reinterpret_cast<const double2*>(Ld + ldblk(bi + 1, pn) + g * 8 + 2 * t);
+                b0 = vb.x;
+                b1 = vb.y;
+            }
+            for (int q = 0; q < pn; ++q) {
+                const double2 bq = *reinterpret_cast<const double2*>(Ld + ldblk(pn, q) + g * 8 + 2 * t);
+                const double2 aq = *reinterpret_cast<const double2*>(Ld + ldblk(bi, q) + g * 8 + 2 * t);
+                dmma884(a0, a1, aq.x, bq.x);
+                dmma884(a0, a1, aq.y, bq.y);
+                if (two) {
+                    const double2 cq = *reinterpret_cast<const double2*>(Ld + ldblk(bi + 1, q) + g * 8 + 2 * t);
+                    dmma884(b0, b1, cq.x, bq.x);
+                    dmma884(b0, b1, cq.y, bq.y);
+                }
+            }
+            if (!live0) a0 = b0 = 0.0;
+            if (!live1) a1 = b1 = 0.0;
+            double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
+            dmma884(x0, x1, a0, dv.x);
+            dmma884(x0, x1, a1, dv.y);
+            *reinterpret_cast<double2*>(Ld + ldblk(bi, pn) + g * 8 + 2 * t) = make_double2(x0, x1);
+            if (two) {
+                dmma884(y0, y1, b0, dv.x);
+                dmma884(y0, y1, b1, dv.y);
+                *reinterpret_cast<double2*>(Ld + ldblk(bi + 1, pn) + g * 8 + 2 * t) = make_double2(y0, y1);
+            }
+        }
+        __syncwarp();
+    }
+    return 0;
+}
+
 // DBG (timing experiments, compiled only with -DMF_EXPERIMENTS; results are garbage): bit mask,
 //   1024 = no ring traffic (no TMA loads, no waits: the loop reads whatever the stages hold),
 //   4096 = TMA loads issued as usual but nobody waits for them,
@@ -345,8 +455,24 @@ __device__ __forceinline__ void potf2_panels(const double* Aw, double* Ld, doubl
 // minus-inverses of L_jj's diagonal blocks are recomputed by every CTA from L_jj with the same
 // routine.  One group barrier per MATRIX.  Few large matrices (n = 30000, B = 1 or 64) or a small
 // ensemble then fill the GPU instead of one SM per matrix.
-template <int NSTAGE, int MINB, int DBG, int COOP, int NMI>
+// LA = 1 (one CTA per matrix, 128-row tiles only): LOOK-AHEAD on the diagonal block.  Without it the
+// 64 x 64 diagonal block of every block column is a serial phase of the whole CTA: eight warps take
+// turns on a chain of 64 dependent pivots while their accumulators wait (ncu: 8 % of all warp time is
+// spent waiting inside that phase, and the co-resident CTA alone cannot keep the tensor pipe full
+// meanwhile).  With it, tile 0 is contracted as before (diagonal block + the 64 rows below it); then
+// the diagonal block goes to shared memory in the block layout, ONE warp (warp 7) factorises it in
+// place - the same arithmetic, panel by panel (potf2_one_warp) - and every warp PARKS its fragment of
+// the 64 lower rows in its registers.  With the other half of their accumulators warps 0-6 contract a
+// half tile meanwhile (tile 1: 112 rows, seven warps) through the same TMA ring; they
+// meet again at the triangular solve, which needs L_jj (mbarrier bar_ljj) and finishes both fragments;
+// from tile 2 on all eight warps work on 128-row tiles.  A chunk of tile 1 is released by seven warps;
+// warp 6 counts twice, so "the eighth release refills the stage" holds for every tile.  Warp 7 steps
+// its ring position over tile 1's chunks, but only once warps 0-6 are through them (bar_t1): a ring wait
+// names its phase by parity alone, and a warp two phases away from the others would read the wrong one.
+template <int NSTAGE, int MINB, int DBG, int COOP, int NMI, int LA = 0>
 __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid_constant__ Params p) {
+    static_assert(!LA || (!COOP && NMI == 2), "look-ahead: one CTA per matrix, 128-row tiles");
+    constexpr int T1 = 112;                    // rows of the look-ahead tile of warps 0-6 (7 x 2 fragments)
     // NMI 8-row fragments per warp: tiles of 64 * NMI rows (NMI = 1: 80 registers, three CTAs per SM)
     constexpr int TM = 64 * NMI;
     constexpr int STAGE_BYTES = (TM + NB) * KC * 8;
@@ -405,7 +531,14 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
         // diagonal-block factorisation: one mbarrier per 8-column panel, the failed-pivot word
         for (int q = 0; q < 8; ++q) mbar_init(smem_u32(smem + OFF_RED + 320) + 8 * q, 1);
         *reinterpret_cast<int*>(smem + OFF_RED + 384) = 0;
+        if (LA) {
+            mbar_init(smem_u32(smem + OFF_RED + 448), 1);       // L_jj is factorised (warp 7 arrives)
+            mbar_init(smem_u32(smem + OFF_RED + 456), 7);       // warps 0-6 are through tile 1's contraction
+        }
     }
+    const uint32_t bar_ljj = smem_u32(smem + OFF_RED + 448), bar_t1 = smem_u32(smem + OFF_RED + 456);
+    volatile int* const la_failword = reinterpret_cast<volatile int*>(smem + OFF_RED + 384);
+    uint32_t ljj_par = 0, t1_par = 0;
     __syncthreads();
     uint32_t use_s = 0, use_k = 0;
     uint32_t potf2_parity = 0;
@@ -479,7 +612,10 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 known[3] = (jb > 0 && ld_acquire(gsync + 2) == ordinal + 1) ? (int)ld_acquire(gsync + 3) : 0;
             const int j0 = jb * NB;
             const int nv = min(NB, n - j0);
-            const int ntile = (n + 1 - j0 + TM - 1) / TM;
+            // look-ahead: tile 0 = 128 rows, tile 1 = up to 56 rows (the half tile), then 128-row tiles
+            const int la_below = n + 1 - (j0 + TM);
+            const int ntile = LA ? 1 + (la_below > 0 ? 1 + (la_below > T1 ? (la_below - T1 + TM - 1) / TM : 0) : 0)
+                                 : (n + 1 - j0 + TM - 1) / TM;
             const int nk = j0 / KC;
             const int nicols = (nv + 7) >> 3;     // 8-column groups that hold real columns
             // rows written by the slowest warp in the previous block column must be in
@@ -487,6 +623,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
             // the first barrier of the contraction loop); also fences the stage area
             __syncthreads();
             if (COOP && known[3]) fail = known[3];
+            if (LA) fail = *la_failword;          // a failed pivot of the previous diagonal block (warp 7 met it)
             if (fail) break;
             // The rows of L this block column streams were written through the generic proxy by
             // all threads (ordered by the barrier above); a thread that issues TMA loads must
@@ -516,18 +653,25 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                     if (ld_acquire(gsync + 2) == ordinal + 1) return cols;
                 return (int)(v - seq0);
             };
+            double acc[2][8][2];                   // (declared here: fragment 1 of tile 0 outlives the tile in LA)
             for (int it = it_first; it < ntile; it += G) {
-                const int i0 = j0 + it * TM;
+                const bool half = LA && it == 1;
+                if (half && warp_u == 7) continue;                     // warp 7 is in the diagonal block
+                const int i0 = LA ? (it == 0 ? j0 : (it == 1 ? j0 + TM : j0 + TM + T1 + TM * (it - 2))) : j0 + it * TM;
+                // first row of the NEXT tile of the block column and whether it is the half tile
+                const int r_next = LA ? (it == 0 ? j0 + TM : (it == 1 ? j0 + TM + T1 : i0 + TM)) : i0 + G * TM;
+                const int rb8 = half ? warp_u : tbw;                   // 8-row block of fragment 0 in this tile
+                const int fs = half ? 56 : 64;                         // rows between the warp's two fragments
                 // Rows of the tile are dealt to the warps in 8-row fragments: fragment mi of warp w
                 // is rows 8 tb(w) + 64 mi .. + 7 with tb = 0,1,2,3,7,6,5,4.  Warps w and w + 4 share
                 // an SM sub-partition, so every sub-partition gets the same tensor work both in the
                 // diagonal tile (triangle blocks s and 7 - s: s + 1 and 8 - s column groups) and in
                 // the ragged last tile of a block column (valid fragments spread round-robin).
-                const int wrow0 = i0 + 8 * tbw;                // first row of fragment 0; fragment 1 is 64 below
+                const int wrow0 = i0 + 8 * rb8;                // first row of fragment 0; fragment 1 is 64 below
                 // 8-column groups this warp has to produce: none if its rows lie beyond the
                 // residual row, only the lower triangle inside the diagonal block
                 int nil0 = (wrow0 > n) ? 0 : nicols;
-                const int nil1 = (NMI < 2 || wrow0 + 64 > n) ? 0 : nicols;
+                const int nil1 = (NMI < 2 || wrow0 + fs > n) ? 0 : nicols;
                 if (it == 0) nil0 = min(nil0, tbw + 1);
                 int fenced = 0;                                        // per thread, per tile
                 if (COOP) {
@@ -590,15 +734,16 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                         // refill are warp-uniform code
                         __syncwarp();
                         unsigned old = 0;
-                        atoms_inc_lane0(old, smem_u32(released) + 4 * use_s, lane);
+                        const unsigned inc = (half && warp_u == 6) ? 2u : 1u;      // (also for warp 7, see LA)
+                        atoms_add_lane0(old, smem_u32(released) + 4 * use_s, inc, lane);
                         old = __reduce_max_sync(0xffffffffu, old);
-                        if ((old & 7) == 7) {
+                        if (((old + inc) & 7u) == 0u) {
                             int tk = kc + NSTAGE, r0 = i0;
                             bool go = true;
                             if (tk >= nk) {
                                 tk -= nk;
-                                r0 = i0 + TM;
-                                go = (it > 0) && (it + 1 < ntile);
+                                r0 = r_next;
+                                go = (LA || it > 0) && (it + 1 < ntile);
                             }
                             if (go && !(DBG & 1024))
                                 tma_chunk_elect(stage_u32 + use_s * STAGE_BYTES, NMI == 2 ? &p.tmap128 : &p.tmap, &p.tmap,
@@ -638,7 +783,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                     if (tid < TM) {
                         const bool same = it + G < ntile;
                         const int pj = same ? j0 : j0 + NB;
-                        const int prow = (same ? i0 + G * TM : j0 + NB) + tid;
+                        const int prow = (same ? r_next : j0 + NB) + tid;
                         if (prow < n && pj < n) {
                             const unsigned bytes = (unsigned)min(NB, (int)ld - pj) * 8u;
                             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Kb + (size_t)prow * ld + pj), "r"(bytes) : "memory");
@@ -648,8 +793,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 prefetch_next_k();
 
                 // accumulators start at -K(tile); the residual enters as row n
-                double acc[2][8][2];
-                const bool interior = (it > 0) && (i0 + TM <= n) && (j0 + NB <= n);
+                const bool interior = (it > 0) && (i0 + (half ? T1 : TM) <= n) && (j0 + NB <= n);
                 if ((DBG & 128) && interior) {
 #pragma unroll
                     for (int mi = 0; mi < NMI; ++mi)
@@ -658,7 +802,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 } else if (interior) {
 #pragma unroll
                     for (int mi = 0; mi < NMI; ++mi) {
-                        const double* src = Kb + (size_t)(wrow0 + 64 * mi + g) * ld + j0 + 2 * t;
+                        const double* src = Kb + (size_t)(wrow0 + fs * mi + g) * ld + j0 + 2 * t;
 #pragma unroll
                         for (int ni = 0; ni < 8; ++ni) {
                             const double2 v = *reinterpret_cast<const double2*>(src + 8 * ni);
@@ -669,7 +813,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 } else {
 #pragma unroll
                     for (int mi = 0; mi < NMI; ++mi) {
-                        const int row = wrow0 + 64 * mi + g;
+                        const int row = wrow0 + fs * mi + g;
 #pragma unroll
                         for (int ni = 0; ni < 8; ++ni) {
                             const int col = j0 + 8 * ni + 2 * t;
@@ -687,6 +831,60 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                     }
                 }
 
+                // The triangular solve against L_jj and the store of the finished rows, for fragment 0 at
+                // row r0 and fragment 1 at row r1 (a0 / a1: the fragment holds rows that need it).
+                auto finish_rows = [&](int r0, bool a0, int r1, bool a1) {
+                    const bool dead = LA && *la_failword != 0;     // the diagonal block failed: nothing to finish
+                    const bool act[2] = {a0 && !dead, a1 && !dead};
+                    if (!act[0] && !act[1]) return;
+
+                // ---- X = C L_jj^-T on the tensor cores, 8-column blocks, in registers.
+                // acc holds -C; Dinv holds -inv(L_bb), so x = acc Dinv^T = +X, and the later
+                // column groups (still negated) absorb +X L^T ----
+#pragma unroll
+                for (int nb = 0; nb < 8; ++nb) {
+                    if (DBG & 64) break;
+                    const double2 dv = *reinterpret_cast<const double2*>(Dinv + nb * 64 + g * 8 + 2 * t);
+#pragma unroll
+                    for (int mi = 0; mi < NMI; ++mi) {
+                        if (!act[mi]) continue;
+                        double x0 = 0.0, x1 = 0.0;
+                        dmma884(x0, x1, acc[mi][nb][0], dv.x);
+                        dmma884(x0, x1, acc[mi][nb][1], dv.y);
+                        acc[mi][nb][0] = x0;
+                        acc[mi][nb][1] = x1;
+                    }
+#pragma unroll
+                    for (int nb2 = nb + 1; nb2 < 8; ++nb2) {
+                        const double2 lv = *reinterpret_cast<const double2*>(Ld + ldblk(nb2, nb) + g * 8 + 2 * t);
+#pragma unroll
+                        for (int mi = 0; mi < NMI; ++mi) {
+                            if (!act[mi]) continue;
+                            dmma884(acc[mi][nb2][0], acc[mi][nb2][1], acc[mi][nb][0], lv.x);
+                            dmma884(acc[mi][nb2][0], acc[mi][nb2][1], acc[mi][nb][1], lv.y);
+                        }
+                    }
+                }
+
+                // ---- rows of L (and z) are final: write them once ----
+#pragma unroll
+                for (int mi = 0; mi < NMI; ++mi) {
+                    const int row = (mi ? r1 : r0) + g;
+                    if ((DBG & 512) && row < n - 1) continue;
+                    if (act[mi] && row <= n) {
+#pragma unroll
+                        for (int ni = 0; ni < 8; ++ni) {
+                            const int col = j0 + 8 * ni + 2 * t;
+                            double* dst = Kb + (size_t)row * ld + col;
+                            if (col + 1 < n)
+                                *reinterpret_cast<double2*>(dst) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+                            else if (col < n)
+                                dst[0] = acc[mi][ni][0];
+                        }
+                    }
+                }
+                fence_async_proxy();              // X -> async proxy
+                };
                 // ---- contraction over the finished columns k < j0 (tensor cores) ----
                 for (int kc = 0; kc < nk; ++kc) {
                     if (DBG & 8) {          // timing experiment: consume the ring without computing
@@ -703,7 +901,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                         const int choff = ((4 * h + t) ^ gp) << 4;
 #pragma unroll
                         for (int mi = 0; mi < NMI; ++mi)
-                            a[mi] = *reinterpret_cast<const double2*>(sb + (8 * tbw + 64 * mi + gp) * 128 + choff);
+                            a[mi] = *reinterpret_cast<const double2*>(sb + (8 * rb8 + fs * mi + gp) * 128 + choff);
 #pragma unroll
                         for (int nq = 0; nq < 2; ++nq) {
                             // warp-uniform block-level branches (not per-instruction predicates): they
@@ -758,6 +956,69 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 }
                 // acc now holds S - K = -C
 
+                if (LA && it == 0) {
+                    // ---- look-ahead: MINUS C, lower 8 x 8 blocks, straight into the layout the
+                    // factorisation works in; warp 7 factorises, the others go on to the half tile ----
+#pragma unroll
+                    for (int ni = 0; ni < 8; ++ni)
+                        if (ni <= tbw)
+                            *reinterpret_cast<double2*>(Ld + ldblk(tbw, ni) + g * 8 + 2 * t) = make_double2(acc[0][ni][0], acc[0][ni][1]);
+                    const int prow1 = wrow0 + 64;              // first row of fragment 1
+                    if (ntile > 1 && warp_u != 7 && prow1 + g <= n) {
+                        // Warps 0-6 need all their accumulators for the next tile: fragment 1 (MINUS C,
+                        // not yet solved) is parked where its X will go; the same thread reads it back.
+#pragma unroll
+                        for (int ni = 0; ni < 8; ++ni) {
+                            const int col = j0 + 8 * ni + 2 * t;
+                            double* dst = Kb + (size_t)(prow1 + g) * ld + col;
+                            if (col + 1 < n)
+                                *reinterpret_cast<double2*>(dst) = make_double2(acc[1][ni][0], acc[1][ni][1]);
+                            else if (col < n)
+                                dst[0] = acc[1][ni][0];
+                        }
+                    }
+                    __syncthreads();
+                    if (warp_u == 7) {
+                        const int f7 = potf2_one_warp<DBG>(Ld, Dinv, colbuf, nv, j0);
+                        if (f7) {
+                            if (lane == 0) *la_failword = f7;
+                        } else {
+                            // the inverses the row tiles multiply by, then L_jj (and the z entries inside
+                            // it, when the block column is the last one) back to global memory
+                            __syncwarp();
+                            dinv_blocks(Ld, Dinv, lane);
+                            dinv_blocks(Ld, Dinv, lane + 32);
+                            const int cp = 2 * lane, col = j0 + cp;
+                            for (int rr = 0; rr < NB; ++rr) {
+                                const int row = j0 + rr;
+                                if (row <= n && col < n) {
+                                    double2 v = make_double2(0.0, 0.0);
+                                    if ((cp >> 3) <= (rr >> 3))
+                                        v = *reinterpret_cast<const double2*>(Ld + ldblk(rr >> 3, cp >> 3) + (rr & 7) * 8 + (cp & 7));
+                                    double* dst = Kb + (size_t)row * ld + col;
+                                    if (col + 1 < n)
+                                        *reinterpret_cast<double2*>(dst) = v;
+                                    else
+                                        dst[0] = v.x;
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_ljj);   // L_jj and the inverses are in place (or the block failed)
+                        finish_rows(0, false, prow1, prow1 <= n);
+                        if (ntile > 1) {                        // step over the chunks of the half tile
+                            mbar_wait(bar_t1, t1_par);
+                            const uint32_t tot = use_s + (uint32_t)nk;
+                            use_k += tot / NSTAGE;
+                            use_s = tot % NSTAGE;
+                        }
+                        continue;
+                    }
+                    if (ntile > 1) continue;        // tile 1 first; the parked fragment is finished after it
+                    mbar_wait(bar_ljj, ljj_par);
+                    finish_rows(0, false, prow1, prow1 <= n);
+                    continue;
+                }
                 if (it == 0) {
                     // ---- diagonal block: Cholesky of C[0:64, 0:64] ----
                     // (a CTA that ran ahead of a failed block column must not factorise garbage)
@@ -929,56 +1190,39 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                     for (int s0 = 0; s0 < NSTAGE; ++s0)
                         if (s0 < nk) tma_chunk((use_s + s0) % NSTAGE, s0, i0 + G * TM);
                 }
-                // fragments that still need the solve: real rows, not part of the diagonal block
-                const bool act[2] = {it > 0 && wrow0 <= n, NMI == 2 && wrow0 + 64 <= n};
-                if (!act[0] && !act[1]) continue;
-
-                // ---- X = C L_jj^-T on the tensor cores, 8-column blocks, in registers.
-                // acc holds -C; Dinv holds -inv(L_bb), so x = acc Dinv^T = +X, and the later
-                // column groups (still negated) absorb +X L^T ----
-#pragma unroll
-                for (int nb = 0; nb < 8; ++nb) {
-                    if (DBG & 64) break;
-                    const double2 dv = *reinterpret_cast<const double2*>(Dinv + nb * 64 + g * 8 + 2 * t);
-#pragma unroll
-                    for (int mi = 0; mi < NMI; ++mi) {
-                        if (!act[mi]) continue;
-                        double x0 = 0.0, x1 = 0.0;
-                        dmma884(x0, x1, acc[mi][nb][0], dv.x);
-                        dmma884(x0, x1, acc[mi][nb][1], dv.y);
-                        acc[mi][nb][0] = x0;
-                        acc[mi][nb][1] = x1;
-                    }
-#pragma unroll
-                    for (int nb2 = nb + 1; nb2 < 8; ++nb2) {
-                        const double2 lv = *reinterpret_cast<const double2*>(Ld + ldblk(nb2, nb) + g * 8 + 2 * t);
-#pragma unroll
-                        for (int mi = 0; mi < NMI; ++mi) {
-                            if (!act[mi]) continue;
-                            dmma884(acc[mi][nb2][0], acc[mi][nb2][1], acc[mi][nb][0], lv.x);
-                            dmma884(acc[mi][nb2][0], acc[mi][nb2][1], acc[mi][nb][1], lv.y);
-                        }
-                    }
-                }
-
-                // ---- rows of L (and z) are final: write them once ----
-#pragma unroll
-                for (int mi = 0; mi < NMI; ++mi) {
-                    const int row = wrow0 + 64 * mi + g;
-                    if ((DBG & 512) && row < n - 1) continue;
-                    if (act[mi] && row <= n) {
+                if (half) {
+                    // through the half tile's contraction: warp 7 may use the ring again; then L_jj
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_t1);
+                    mbar_wait(bar_ljj, ljj_par);
+                    finish_rows(wrow0, wrow0 <= n, wrow0 + fs, wrow0 + fs <= n);
+                    // then the fragment of tile 0 this warp parked in global memory (MINUS C, where X goes)
+                    const int prow1 = j0 + 8 * tbw + 64;
+                    if (prow1 <= n && !*la_failword) {
+                        const double* src = Kb + (size_t)(prow1 + g) * ld + j0 + 2 * t;
 #pragma unroll
                         for (int ni = 0; ni < 8; ++ni) {
                             const int col = j0 + 8 * ni + 2 * t;
-                            double* dst = Kb + (size_t)row * ld + col;
-                            if (col + 1 < n)
-                                *reinterpret_cast<double2*>(dst) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-                            else if (col < n)
-                                dst[0] = acc[mi][ni][0];
+                            double2 v = make_double2(0.0, 0.0);
+                            if (prow1 + g <= n) {
+                                if (col + 1 < n)
+                                    v = *reinterpret_cast<const double2*>(src + 8 * ni);
+                                else if (col < n)
+                                    v.x = src[8 * ni];
+                            }
+                            acc[1][ni][0] = v.x;
+                            acc[1][ni][1] = v.y;
                         }
+                        finish_rows(0, false, prow1, true);
                     }
+                } else {
+                    // fragments that still need the solve: real rows, not part of the diagonal block
+                    finish_rows(wrow0, it > 0 && wrow0 <= n, wrow0 + 64, NMI == 2 && wrow0 + 64 <= n);
                 }
-                fence_async_proxy();              // X -> async proxy
+            }
+            if (LA) {
+                ljj_par ^= 1u;
+                if (ntile > 1) t1_par ^= 1u;
             }
         }
 
@@ -993,6 +1237,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
             if (rank != 0) continue;  // CTA 0 of the group finishes alone
         }
         __syncthreads();
+        if (LA) fail = *la_failword;
         double q = 0.0, lg = 0.0;
         if (!fail) {
             const double* z = Kb + (size_t)n * ld;
@@ -1018,6 +1263,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
             }
             p.ll[mat] = fail ? -INFINITY : (-0.5 * s - logdet - 0.5 * (double)n * log(2.0 * 3.141592653589793));
             p.info[mat] = fail;
+            if (LA) *la_failword = 0;
         }
         __syncthreads();
     }
@@ -1164,6 +1410,16 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
         }
     }
     MF_CUDA_CHECK(h, cudaMemsetAsync(h->coop_sync, 0, sizeof(int), st));      // p.counter
+    // Batches that fill the GPU with 128-row tiles: the look-ahead instantiation (the diagonal block
+    // of every block column is factorised by one warp behind a half tile's contraction).
+    // potrf_lookahead = 1 keeps the plain kernel (tests compare the two bit for bit).
+    if (!small_tiles && experiment == 0 && h->opt.potrf_lookahead != 1) {
+        MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<3, 2, 0, 0, 2, 1>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, pf::smem_bytes(3)));
+        pf::mf_potrf_ll_kernel<3, 2, 0, 0, 2, 1><<<grid, pf::THREADS, pf::smem_bytes(3), st>>>(p);
+        MF_CUDA_CHECK(h, cudaGetLastError());
+        return MF_OK;
+    }
     if (small_tiles) {
         const int grid1 = batch < cta_slots ? batch : cta_slots;
         MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<3, 3, 0, 0, 1>,
