@@ -513,3 +513,50 @@ def test_samples_have_the_covariance_they_are_drawn_from(mf):
     Xj = gj.sample(a, [0.5, 0.2, 0.3], size=draws, seed=1)
     Kj = gj.compute_matrix(a, [0.5, 0.2, 0.3])
     assert np.abs(Xj.T @ Xj / draws - Kj).max() <= 6.0 * np.abs(Kj).max() * np.sqrt(2.0 / draws)
+
+
+@pytest.mark.parametrize("N", [43, 64, 81, 100, 150, 213, 400])
+def test_lookahead_kernel_matches_plain_kernel(mf, N):
+    """Batches that fill the GPU with 128-row tiles take the look-ahead instantiation of the
+    factorisation (the diagonal block of every block column factorised by one warp behind the next
+    tile, a fragment parked in place meanwhile): same factor, z, log-likelihood and info, bit for
+    bit, as the plain one-CTA-per-matrix kernel - failures included - at sizes that walk the tile
+    boundaries (no tile 1, a ragged tile 1, ragged 128-row tiles), and within 1e-9 of the oracle."""
+    from miniframe_b200._engine import Engine
+    eng = Engine.get()
+    t, (rv, rhk, bis), (e1, e2, e3) = go.synthetic_series(N, seed=100 + N)
+    gp = mf.BIGgp.BIGgp(mf.kernels.SquaredExponential, [None, None, None], t, rv, e1, rhk, e2, bis, e3)
+    n = 3 * N
+    B = 330                                         # more than 2 x 148 CTAs: the persistent loop hands out
+    rng = np.random.default_rng(N)
+    A = np.column_stack([rng.uniform(2, 30, B), rng.uniform(0.01, 0.5, B)] + [rng.uniform(0.2, 1.5, B)] * 5)
+    A[3] = A[200] = A[-1] = [5000.0, 0.0, 1e8, 1e8, 1e8, 1e8, 1e8]          # not positive definite in FP64
+    prob = gp._problem(N)
+    resid = eng.tensor(go.biggp_y(rv, rhk, bis)[None, :])
+    out = {}
+    try:
+        eng.set_option("potrf_group", 1)
+        eng.set_option("potrf_tile", 2)
+        for la in (1, 2):
+            eng.set_option("potrf_lookahead", la)
+            Kd = eng.build_cov(prob, eng.tensor(t), eng.tensor(gp._diag_yerr()), eng.tensor(A), None, full=False)
+            ll, info = eng.potrf_loglike(Kd, n, resid)
+            out[la] = (Kd.cpu().numpy(), ll.cpu().numpy(), info.cpu().numpy())
+    finally:
+        eng.set_option("potrf_group", 0)
+        eng.set_option("potrf_tile", 0)
+        eng.set_option("potrf_lookahead", 0)
+    (K1, ll1, i1), (K2, ll2, i2) = out[1], out[2]
+    assert np.array_equal(i1, i2)
+    bad = i1 != 0
+    assert bad[3] and bad[200] and bad[-1]
+    ok = np.nonzero(~bad)[0]
+    assert ok.size >= B - 8
+    for b in ok[:: max(1, ok.size // 40)]:
+        assert np.array_equal(np.tril(K1[b, :n, :n]), np.tril(K2[b, :n, :n]))
+        assert np.array_equal(K1[b, n, :n], K2[b, n, :n])
+    assert np.array_equal(ll1[ok], ll2[ok]) and np.all(np.isinf(ll2[bad])) and np.all(ll2[bad] < 0)
+    y = go.biggp_y(rv, rhk, bis)
+    for b in ok[[0, ok.size // 2, -1]]:
+        want = go.biggp_loglike_literal("SquaredExponential", A[b], t, y, e1, e2, e3)
+        assert rel_err(float(ll2[b]), want) <= LL_RTOL
