@@ -818,22 +818,30 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                         }
                     }
                 } else {
+                    // Diagonal, ragged and last-column tiles: entries above the diagonal, beyond the
+                    // matrix or in rows beyond the residual start at zero.  Every load is issued
+                    // unconditionally (an entry that does not count reads a harmless address and is
+                    // dropped by a select): guarded loads serialised 32 memory latencies per thread
+                    // here, 2.2 % of all warp time (ncu).
 #pragma unroll
                     for (int mi = 0; mi < NMI; ++mi) {
                         const int row = wrow0 + fs * mi + g;
+                        const bool mrow = row < n, rrow = (row == n) && (rb != nullptr);
+                        const double* const rowp = mrow ? Kb + (size_t)row * ld : (rrow ? rb : Kb);
+                        double v[8][2];
+                        bool ok[8][2];
+#pragma unroll
+                        for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int col = j0 + 8 * ni + 2 * t + e;
+                                ok[ni][e] = col < n && ((mrow && col <= row) || rrow);
+                                v[ni][e] = rowp[ok[ni][e] ? col : 0];
+                            }
 #pragma unroll
                         for (int ni = 0; ni < 8; ++ni) {
-                            const int col = j0 + 8 * ni + 2 * t;
-                            double v0 = 0.0, v1 = 0.0;
-                            if (row < n) {
-                                if (col <= row && col < n) v0 = Kb[(size_t)row * ld + col];
-                                if (col + 1 <= row && col + 1 < n) v1 = Kb[(size_t)row * ld + col + 1];
-                            } else if (row == n && rb != nullptr) {
-                                if (col < n) v0 = rb[col];
-                                if (col + 1 < n) v1 = rb[col + 1];
-                            }
-                            acc[mi][ni][0] = flip(v0);
-                            acc[mi][ni][1] = flip(v1);
+                            acc[mi][ni][0] = flip(ok[ni][0] ? v[ni][0] : 0.0);
+                            acc[mi][ni][1] = flip(ok[ni][1] ? v[ni][1] : 0.0);
                         }
                     }
                 }
