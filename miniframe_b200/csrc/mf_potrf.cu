@@ -455,7 +455,8 @@ __device__ __forceinline__ int potf2_one_warp(double* Ld, double* Dinv, double* 
 // minus-inverses of L_jj's diagonal blocks are recomputed by every CTA from L_jj with the same
 // routine.  One group barrier per MATRIX.  Few large matrices (n = 30000, B = 1 or 64) or a small
 // ensemble then fill the GPU instead of one SM per matrix.
-// LA = 1 (one CTA per matrix, 128-row tiles only): LOOK-AHEAD on the diagonal block.  Without it the
+// LA = 1 (one CTA per matrix): LOOK-AHEAD on the diagonal block, described for the 128-row tiles
+// (NMI = 2; on 64-row tiles tile 0 IS the diagonal block, nothing is parked, tile 1 has 56 rows).  Without it the
 // 64 x 64 diagonal block of every block column is a serial phase of the whole CTA: eight warps take
 // turns on a chain of 64 dependent pivots while their accumulators wait (ncu: 8 % of all warp time is
 // spent waiting inside that phase, and the co-resident CTA alone cannot keep the tensor pipe full
@@ -479,8 +480,8 @@ __device__ __forceinline__ int potf2_one_warp(double* Ld, double* Dinv, double* 
 // as the phase it hides is long).
 template <int NSTAGE, int MINB, int DBG, int COOP, int NMI, int LA = 0>
 __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid_constant__ Params p) {
-    static_assert(!LA || (!COOP && NMI == 2), "look-ahead: one CTA per matrix, 128-row tiles");
-    constexpr int T1 = 112;                    // rows of the look-ahead tile of warps 0-6 (7 x 2 fragments)
+    static_assert(!LA || !COOP, "look-ahead: one CTA per matrix");
+    constexpr int T1 = 56 * NMI;               // rows of the look-ahead tile of warps 0-6 (7 x NMI fragments)
     // NMI 8-row fragments per warp: tiles of 64 * NMI rows (NMI = 1: 80 registers, three CTAs per SM)
     constexpr int TM = 64 * NMI;
     constexpr int STAGE_BYTES = (TM + NB) * KC * 8;
@@ -979,7 +980,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                         if (ni <= tbw)
                             *reinterpret_cast<double2*>(Ld + ldblk(tbw, ni) + g * 8 + 2 * t) = make_double2(acc[0][ni][0], acc[0][ni][1]);
                     const int prow1 = wrow0 + 64;              // first row of fragment 1
-                    if (ntile > 1 && warp_u != 7 && prow1 + g <= n) {
+                    if (NMI == 2 && ntile > 1 && warp_u != 7 && prow1 + g <= n) {
                         // Warps 0-6 need all their accumulators for the next tile: fragment 1 (MINUS C,
                         // not yet solved) is parked where its X will go; the same thread reads it back.
 #pragma unroll
@@ -1020,7 +1021,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                         }
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_ljj);   // L_jj and the inverses are in place (or the block failed)
-                        finish_rows(0, false, prow1, prow1 <= n);
+                        finish_rows(0, false, prow1, NMI == 2 && prow1 <= n);
                         if (ntile > 1) {                        // step over the chunks of tile 1
                             mbar_wait(bar_t1, t1_par);
                             const uint32_t tot = use_s + (uint32_t)nk;
@@ -1031,7 +1032,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                     }
                     if (ntile > 1) continue;        // tile 1 first; the parked fragment is finished after it
                     mbar_wait(bar_ljj, ljj_par);
-                    finish_rows(0, false, prow1, prow1 <= n);
+                    finish_rows(0, false, prow1, NMI == 2 && prow1 <= n);
                     continue;
                 }
                 if (it == 0) {
@@ -1210,10 +1211,10 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_t1);
                     mbar_wait(bar_ljj, ljj_par);
-                    finish_rows(wrow0, wrow0 <= n, wrow0 + fs, wrow0 + fs <= n);
+                    finish_rows(wrow0, wrow0 <= n, wrow0 + fs, NMI == 2 && wrow0 + fs <= n);
                     // then the fragment of tile 0 this warp parked in global memory (MINUS C, where X goes)
                     const int prow1 = j0 + 8 * tbw + 64;
-                    if (prow1 <= n && !*la_failword) {
+                    if (NMI == 2 && prow1 <= n && !*la_failword) {
                         const double* src = Kb + (size_t)(prow1 + g) * ld + j0 + 2 * t;
 #pragma unroll
                         for (int ni = 0; ni < 8; ++ni) {
@@ -1432,6 +1433,14 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
         MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<3, 2, 0, 0, 2, 1>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, pf::smem_bytes(3)));
         pf::mf_potrf_ll_kernel<3, 2, 0, 0, 2, 1><<<grid, pf::THREADS, pf::smem_bytes(3), st>>>(p);
+        MF_CUDA_CHECK(h, cudaGetLastError());
+        return MF_OK;
+    }
+    if (small_tiles && experiment == 0 && h->opt.potrf_lookahead != 1) {
+        const int grid1 = batch < cta_slots ? batch : cta_slots;
+        MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<3, 3, 0, 0, 1, 1>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem));
+        pf::mf_potrf_ll_kernel<3, 3, 0, 0, 1, 1><<<grid1, pf::THREADS, tile_smem, st>>>(p);
         MF_CUDA_CHECK(h, cudaGetLastError());
         return MF_OK;
     }

@@ -29,7 +29,7 @@ st = eng.stream()
 row_n = ctypes.c_void_p(ws.data_ptr() + n * ld * 8)
 out = {}
 eng.set_option("potrf_group", 1)
-eng.set_option("potrf_tile", 2)
+eng.set_option("potrf_tile", int(os.environ.get("TILE", "2")))
 for name, opt in (("plain", 1), ("lookahead", 2)):
     eng.set_option("potrf_lookahead", opt)
     ll = torch.empty(B, dtype=torch.float64, device="cuda"); info = torch.empty(B, dtype=torch.int32, device="cuda")

@@ -515,19 +515,21 @@ def test_samples_have_the_covariance_they_are_drawn_from(mf):
     assert np.abs(Xj.T @ Xj / draws - Kj).max() <= 6.0 * np.abs(Kj).max() * np.sqrt(2.0 / draws)
 
 
+@pytest.mark.parametrize("tile", [2, 1])
 @pytest.mark.parametrize("N", [43, 64, 81, 100, 150, 213, 400])
-def test_lookahead_kernel_matches_plain_kernel(mf, N):
-    """Batches that fill the GPU with 128-row tiles take the look-ahead instantiation of the
-    factorisation (the diagonal block of every block column factorised by one warp behind the next
-    tile, a fragment parked in place meanwhile): same factor, z, log-likelihood and info, bit for
-    bit, as the plain one-CTA-per-matrix kernel - failures included - at sizes that walk the tile
-    boundaries (no tile 1, a ragged tile 1, ragged 128-row tiles), and within 1e-9 of the oracle."""
+def test_lookahead_kernel_matches_plain_kernel(mf, N, tile):
+    """Batches that fill the GPU take the look-ahead instantiation of the factorisation (the
+    diagonal block of every block column factorised by one warp behind the next tile; on 128-row
+    tiles a fragment is parked in place meanwhile): same factor, z, log-likelihood and info, bit
+    for bit, as the plain one-CTA-per-matrix kernel - failures included - on both tile heights, at
+    sizes that walk the tile boundaries (no tile 1, a ragged tile 1, ragged later tiles), and
+    within 1e-9 of the oracle."""
     from miniframe_b200._engine import Engine
     eng = Engine.get()
     t, (rv, rhk, bis), (e1, e2, e3) = go.synthetic_series(N, seed=100 + N)
     gp = mf.BIGgp.BIGgp(mf.kernels.SquaredExponential, [None, None, None], t, rv, e1, rhk, e2, bis, e3)
     n = 3 * N
-    B = 330                                         # more than 2 x 148 CTAs: the persistent loop hands out
+    B = 330 if tile == 2 else 470                   # more than 2 (3) x 148 CTAs: the persistent loop hands out
     rng = np.random.default_rng(N)
     A = np.column_stack([rng.uniform(2, 30, B), rng.uniform(0.01, 0.5, B)] + [rng.uniform(0.2, 1.5, B)] * 5)
     A[3] = A[200] = A[-1] = [5000.0, 0.0, 1e8, 1e8, 1e8, 1e8, 1e8]          # not positive definite in FP64
@@ -536,7 +538,7 @@ def test_lookahead_kernel_matches_plain_kernel(mf, N):
     out = {}
     try:
         eng.set_option("potrf_group", 1)
-        eng.set_option("potrf_tile", 2)
+        eng.set_option("potrf_tile", tile)
         for la in (1, 2):
             eng.set_option("potrf_lookahead", la)
             Kd = eng.build_cov(prob, eng.tensor(t), eng.tensor(gp._diag_yerr()), eng.tensor(A), None, full=False)
