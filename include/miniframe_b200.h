@@ -100,7 +100,8 @@ const char* mf_status_string(int status);
  * counter and the group barriers of mf_potrf_loglike), a small cache of TMA
  * descriptors and the last error text, all of which concurrent launches would
  * share.  Calls on one handle must therefore be issued to one stream at a time;
- * different handles are independent (thread-safe across handles). */
+ * different handles are independent (thread-safe across handles).  mf_create also
+ * sets the device's L2 set-aside for persisting lines to 64 MB (see "l2_persist_mb"). */
 int  mf_create(mf_handle_t* out, int device);
 int  mf_destroy(mf_handle_t h);
 const char* mf_last_error(mf_handle_t h);
@@ -111,6 +112,11 @@ int  mf_device_info(mf_handle_t h, int* sm_count, int* cc_major, int* cc_minor);
  *   "potrf_group"  1: one CTA per matrix, G > 1: G CTAs per matrix (cooperative)
  *   "potrf_map"    cooperative factorisation, which CTA takes which row tile:
  *                  1: (tile - block column) mod G, 2: (tile + block column) mod G
+ *   "potrf_lookahead"  one CTA per matrix: 1: the plain kernel, 2: the look-ahead kernel (the
+ *                  diagonal block of a block column factorised by one warp behind the next tile's
+ *                  contraction; bit-identical results)
+ *   "l2_persist_mb"  L2 set-aside (MB, -1: the device maximum) for the rows the factorisation
+ *                  re-reads; a DEVICE limit (cudaLimitPersistingL2CacheSize), 64 MB after mf_create
  *   "cov_ctas"     CTAs per sample of the covariance build
  *   "experiment"   timing-experiment variants; rejected with MF_ERR_UNSUPPORTED
  *                  unless the library was built with -DMF_EXPERIMENTS (the
