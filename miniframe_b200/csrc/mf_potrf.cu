@@ -798,7 +798,9 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                         }
                     }
                 };
-                prefetch_next_k();
+                // (cooperative groups only: with one CTA per matrix the lines were gone from L2 again by
+                // the time the tile started and the prefetch only added traffic - 0.9 % slower, measured)
+                if (COOP) prefetch_next_k();
 
                 // accumulators start at -K(tile); the residual enters as row n
                 const bool interior = (it > 0) && (i0 + (half ? T1 : TM) <= n) && (j0 + NB <= n);
