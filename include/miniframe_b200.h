@@ -100,8 +100,7 @@ const char* mf_status_string(int status);
  * counter and the group barriers of mf_potrf_loglike), a small cache of TMA
  * descriptors and the last error text, all of which concurrent launches would
  * share.  Calls on one handle must therefore be issued to one stream at a time;
- * different handles are independent (thread-safe across handles).  mf_create also
- * sets the device's L2 set-aside for persisting lines to 64 MB (see "l2_persist_mb"). */
+ * different handles are independent (thread-safe across handles). */
 int  mf_create(mf_handle_t* out, int device);
 int  mf_destroy(mf_handle_t h);
 const char* mf_last_error(mf_handle_t h);
@@ -116,7 +115,8 @@ int  mf_device_info(mf_handle_t h, int* sm_count, int* cc_major, int* cc_minor);
  *                  diagonal block of a block column factorised by one warp behind the next tile's
  *                  contraction; bit-identical results)
  *   "l2_persist_mb"  L2 set-aside (MB, -1: the device maximum) for the rows the factorisation
- *                  re-reads; a DEVICE limit (cudaLimitPersistingL2CacheSize), 64 MB after mf_create
+ *                  re-reads; a DEVICE limit (cudaLimitPersistingL2CacheSize), left alone by default:
+ *                  it costs the covariance build half its write bandwidth
  *   "cov_ctas"     CTAs per sample of the covariance build
  *   "experiment"   timing-experiment variants; rejected with MF_ERR_UNSUPPORTED
  *                  unless the library was built with -DMF_EXPERIMENTS (the

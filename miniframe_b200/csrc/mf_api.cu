@@ -83,19 +83,6 @@ extern "C" int mf_create(mf_handle_t* out, int device) {
         delete h;
         return MF_ERR_CUDA;
     }
-    {
-        // L2 set-aside for the lines the factorisation's ring marks evict_last (the block column's own
-        // rows, re-read by every tile of the block column).  Its memory traffic is what takes the
-        // factorisation to the board's power limit (ring off: 536 W, ring on: 979 W at the same tensor
-        // rate); with 64 MB set aside more of those re-reads stay in L2: 0.3 % slower while the clocks
-        // hold, 1 % faster once the power cap bites (mf_set_option "l2_persist_mb" changes it).
-        int maxb = 0;
-        if (cudaDeviceGetAttribute(&maxb, cudaDevAttrMaxPersistingL2CacheSize, device) == cudaSuccess && maxb > 0) {
-            size_t want = (size_t)64 << 20;
-            if (want > (size_t)maxb) want = (size_t)maxb;
-            (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-        }
-    }
     *out = h;
     return MF_OK;
 }
@@ -135,7 +122,9 @@ extern "C" int mf_set_option(mf_handle_t h, const char* name, int value) {
         h->opt.potrf_lookahead = value;
     } else if (!strcmp(name, "l2_persist_mb")) {
         // L2 set-aside for the lines the factorisation's TMA loads mark evict_last (the block column's own
-        // rows, re-read by every tile); -1 = as much as the device allows
+        // rows, re-read by every tile); -1 = as much as the device allows.  Off by default: it is a DEVICE
+        // limit, and 64 MB of it make the factorisation 1 % faster under the board's power cap but halve
+        // the covariance build's write bandwidth (6.9 -> 12.9 ms per 4096 matrices).
         int maxb = 0;
         MF_CUDA_CHECK(h, cudaDeviceGetAttribute(&maxb, cudaDevAttrMaxPersistingL2CacheSize, h->device));
         size_t want = value < 0 ? (size_t)maxb : (size_t)value << 20;
