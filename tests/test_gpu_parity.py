@@ -401,6 +401,12 @@ def test_abi_argument_errors(mf):
     st = eng.lib.mf_potrf_loglike(eng.handle, 1, 12, eng.ptr(buf), 12, 13 * 12, None, 0, eng.ptr(buf),
                                   eng.ptr(buf), eng.stream())
     assert st == 1
+    # options: unknown names and values out of range are refused, the shipped library has no experiments
+    h = eng.handle
+    assert eng.lib.mf_set_option(h, b"no_such_option", 1) == 1
+    assert eng.lib.mf_set_option(h, b"potrf_lookahead", 3) == 1 and eng.lib.mf_set_option(h, b"potrf_tile", 5) == 1
+    assert eng.lib.mf_set_option(h, b"experiment", 8) != 0
+    assert eng.lib.mf_set_option(h, b"potrf_lookahead", 0) == 0 and eng.lib.mf_set_option(h, b"l2_persist_mb", 0) == 0
 
 
 def test_batched_keplerian_and_sine_means(mf, golden):
