@@ -113,7 +113,8 @@ int  mf_device_info(mf_handle_t h, int* sm_count, int* cc_major, int* cc_minor);
  *                  1: (tile - block column) mod G, 2: (tile + block column) mod G
  *   "potrf_lookahead"  one CTA per matrix: 1: the plain kernel, 2: the look-ahead kernel (the
  *                  diagonal block of a block column factorised by one warp behind the next tile's
- *                  contraction; bit-identical results)
+ *                  contraction; bit-identical results); 0: whichever tiling wastes less on the
+ *                  ragged tiles of this matrix order
  *   "l2_persist_mb"  L2 set-aside (MB, -1: the device maximum) for the rows the factorisation
  *                  re-reads; a DEVICE limit (cudaLimitPersistingL2CacheSize), left alone by default:
  *                  it costs the covariance build half its write bandwidth

@@ -82,6 +82,7 @@ struct Params {
     int rd_stride;
     int map_back;         // tile `it` of block column jb goes to CTA (it - jb) mod G instead of (it + jb) mod G
     int* counter;         // next matrix to hand out (one CTA per matrix, zeroed before the launch)
+    int quota;            // most matrices one CTA may take (0: no limit), see mf_potrf_loglike
 };
 
 __device__ __forceinline__ double flip(double x) {      // -x on the integer pipe
@@ -591,8 +592,11 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
     // all CTAs finish together.  (Cooperative groups and the timing-experiment builds stride.)
     constexpr bool DYNAMIC = !COOP;
     int* const next_mat = reinterpret_cast<int*>(red + 16);
+    int taken = 0;
     for (int mat = grp;; mat += ngroups, ++ordinal) {
         if (DYNAMIC) {
+            if (p.quota > 0 && taken >= p.quota) break;       // its fair share is done (CTA-uniform)
+            ++taken;
             if (tid == 0) *next_mat = atomicAdd(p.counter, 1);
             __syncthreads();
             mat = *next_mat;
@@ -1289,6 +1293,35 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
 
 }  // namespace pf
 
+// Row-tile passes (one pass = every warp contracts one 8-row fragment over a chunk; a tile of more
+// than half its height takes two) times chunks, summed over the block columns, for the plain tiling
+// (tiles of `tm` rows from the diagonal block down) and for the look-ahead tiling (tile 0 of tm rows,
+// tile 1 of 7/8 tm rows, then tm-row tiles): where the ragged last tile of a block column falls
+// differs between the two, by up to 7 % of the work at some orders.
+static void mf_tiling_cost(int n, int tm, double* plain, double* lookahead) {
+    const int t1 = tm / 8 * 7;
+    auto tail = [&](long rows) -> long {            // passes of `rows` rows cut into tm-row tiles
+        if (rows <= 0) return 0;
+        const long r = rows % tm;
+        return 2 * (rows / tm) + (r == 0 ? 0 : (r <= tm / 2 ? 1 : 2));
+    };
+    double a = 0.0, b = 0.0;
+    for (int j0 = 0; j0 < n; j0 += 64) {
+        const long R = (long)n + 1 - j0, nk = j0 / 16;
+        a += (double)nk * tail(R);
+        long p = R <= tm / 2 ? 1 : 2;
+        const long below = R - tm;
+        if (below > 0) {
+            const long r1 = below < t1 ? below : t1;
+            p += r1 <= t1 / 2 ? 1 : 2;
+            p += tail(below - t1);
+        }
+        b += (double)nk * p;
+    }
+    *plain = a;
+    *lookahead = b;
+}
+
 extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int64_t ld,
                                 int64_t stride, const double* resid, int64_t resid_stride,
                                 double* ll, int32_t* info, void* stream) {
@@ -1360,6 +1393,7 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
     p.rd_stride = 0;
     p.map_back = h->opt.potrf_map == 2 ? 0 : 1;
     p.counter = reinterpret_cast<int*>(h->coop_sync);
+
     // Tile variant.  Small matrices: 64-row tiles (one 8-row fragment per warp, 80 registers) and
     // THREE CTAs per SM.  The 64 sequential pivots per block column are a latency chain that only
     // other resident matrices can hide, and small matrices are mostly that chain; measured (2664
@@ -1375,6 +1409,28 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
     const int tile_rows = small_tiles ? 64 : 128;
     const int cta_slots = (small_tiles ? 3 : 2) * h->sm_count;
     const int tile_smem = small_tiles ? pf::smem_bytes(3, 1) : pf::smem_bytes(3);
+    // The two CTAs of an SM do not share it fairly: the older one runs at nearly the speed it would
+    // have alone (90 % of the SM at n = 3300), the younger one crawls until the older one has nothing
+    // left to take - and then finishes its matrix alone.  With a handful of waves that tail is a sixth
+    // of the run (592 matrices of order 3300: 264 ms instead of 217).  So with few waves a CTA may not
+    // take more than its share, ceil(batch / CTAs): the old CTA leaves early and the young one gets the
+    // SM; with many waves the tail is short and taking more than one's share is what balances the CTAs
+    // (+4 % at the headline batch).
+    {
+        const int ctas = batch < cta_slots ? batch : cta_slots;
+        const int share = (batch + ctas - 1) / ctas;
+        p.quota = share <= 4 ? share : 0;
+    }
+    // look-ahead or plain kernel (one CTA per matrix): look-ahead hides the diagonal block's pivot chain
+    // (2 - 10 % at the orders measured) unless its tiling wastes more than that on ragged tiles
+    bool lookahead = h->opt.potrf_lookahead != 1;
+    if (h->opt.potrf_lookahead == 0) {
+        double cp = 0.0, cl = 0.0;
+        mf_tiling_cost(n, tile_rows, &cp, &cl);
+        // what hiding the pivot chain is worth shrinks with the order (measured: 11 % at n = 600, 2 % at 1500)
+        const double worth = 60.0 / n < 0.12 ? 60.0 / n : 0.12;
+        lookahead = cl <= (1.0 + worth) * cp;
+    }
     const void* const coop_fn = small_tiles ? (const void*)pf::mf_potrf_ll_kernel<3, 3, 0, 1, 1>
                                             : (const void*)pf::mf_potrf_ll_kernel<3, 2, 0, 1, 2>;
     {
@@ -1431,14 +1487,14 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
     // Batches that fill the GPU with 128-row tiles: the look-ahead instantiation (the diagonal block
     // of every block column is factorised by one warp behind the next tile's contraction).
     // potrf_lookahead = 1 keeps the plain kernel (tests compare the two bit for bit).
-    if (!small_tiles && experiment == 0 && h->opt.potrf_lookahead != 1) {
+    if (!small_tiles && experiment == 0 && lookahead) {
         MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<3, 2, 0, 0, 2, 1>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, pf::smem_bytes(3)));
         pf::mf_potrf_ll_kernel<3, 2, 0, 0, 2, 1><<<grid, pf::THREADS, pf::smem_bytes(3), st>>>(p);
         MF_CUDA_CHECK(h, cudaGetLastError());
         return MF_OK;
     }
-    if (small_tiles && experiment == 0 && h->opt.potrf_lookahead != 1) {
+    if (small_tiles && experiment == 0 && lookahead) {
         const int grid1 = batch < cta_slots ? batch : cta_slots;
         MF_CUDA_CHECK(h, cudaFuncSetAttribute(pf::mf_potrf_ll_kernel<3, 3, 0, 0, 1, 1>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem));

@@ -9,7 +9,8 @@ from miniframe_b200 import kernels
 from miniframe_b200.BIGgp import BIGgp
 from miniframe_b200._engine import Engine
 from oracle import gp_oracle as go
-N, B = 500, 4096
+N, B = int(os.environ.get("NEP", "500")), int(os.environ.get("NB", "4096"))
+REPS = int(os.environ.get("REPS", "10"))
 n = 3 * N
 eng = Engine.get()
 lib, h = eng.lib, eng.handle
@@ -38,7 +39,7 @@ def sampler():
         time.sleep(0.1)
 th = threading.Thread(target=sampler); th.start()
 ms = []
-for rep in range(10):
+for rep in range(REPS):
     lib.mf_build_cov(h, ctypes.byref(prob), B, eng.ptr(t_d), eng.ptr(diag_d), eng.ptr(hyper_d), None, 2, eng.ptr(ws), ld, stride, st)
     lib.mf_interleave_resid(h, B, 3, N, eng.ptr(resid_d), 0, row_n, stride, st)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -48,6 +49,6 @@ for rep in range(10):
 torch.cuda.synchronize(); stop = True; th.join()
 tms = [a.elapsed_time(b) for a, b in ms]
 clk = sorted(s[0] for s in samples); pw = [s[1] for s in samples]
-print("%s: ms %s | last 5 mean %.2f = %.2f TFLOP/s | clocks median %s min %s, power max %.0f W" % (
-    " ".join(sys.argv[1:]) or "default", " ".join("%.1f" % m for m in tms), np.mean(tms[5:]),
-    (n ** 3 / 3 + n ** 2) * B / np.mean(tms[5:]) / 1e9, clk[len(clk) // 2] if clk else None, clk[0] if clk else None, max(pw) if pw else -1))
+print("%s: ms %s | second half mean %.2f = %.2f TFLOP/s | clocks median %s min %s, power max %.0f W" % (
+    " ".join(sys.argv[1:]) or "default", " ".join("%.1f" % m for m in tms), np.mean(tms[REPS // 2:]),
+    (n ** 3 / 3 + n ** 2) * B / np.mean(tms[REPS // 2:]) / 1e9, clk[len(clk) // 2] if clk else None, clk[0] if clk else None, max(pw) if pw else -1))
