@@ -439,6 +439,7 @@ __device__ __forceinline__ int potf2_one_warp(double* Ld, double* Dinv, double* 
 // DBG (timing experiments, compiled only with -DMF_EXPERIMENTS; results are garbage): bit mask,
 //   1024 = no ring traffic (no TMA loads, no waits: the loop reads whatever the stages hold),
 //   4096 = TMA loads issued as usual but nobody waits for them,
+//   16384 = info[] receives the index of the CTA that took the matrix (how the hand-out went),
 //   8 = consume the ring without computing, 32 = skip the diagonal-block factorisation,
 //   64 = skip the triangular solve, 128 = do not load the K tiles, 256 = stream the operands
 //   of every matrix from the first four (L2-resident), 512 = do not store the rows of L
@@ -1284,7 +1285,7 @@ __global__ void __launch_bounds__(THREADS, MINB) mf_potrf_ll_kernel(const __grid
                 logdet += red[8 + w];
             }
             p.ll[mat] = fail ? -INFINITY : (-0.5 * s - logdet - 0.5 * (double)n * log(2.0 * 3.141592653589793));
-            p.info[mat] = fail;
+            p.info[mat] = (DBG & 16384) ? (int)blockIdx.x : fail;      // (experiment: who took which matrix)
             if (LA) *la_failword = 0;
         }
         __syncthreads();
@@ -1556,6 +1557,7 @@ extern "C" int mf_potrf_loglike(mf_handle_t h, int batch, int n, double* K, int6
             case 736: MF_LAUNCH_S(736, xgrid, xsmem); break;
             case 1760: MF_LAUNCH_S(1760, xgrid, xsmem); break;
             case 4832: MF_LAUNCH_S(4832, xgrid, xsmem); break;
+            case 16384: MF_LAUNCH_S(16384, xgrid, xsmem); break;
             default: MF_FAIL(h, MF_ERR_INVALID, "unknown experiment %d", experiment);
         }
     }
