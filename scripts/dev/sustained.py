@@ -24,6 +24,7 @@ t_d, diag_d, hyper_d = eng.tensor(t), eng.tensor(gp._diag_yerr()), eng.tensor(H)
 resid_d = eng.tensor(gp.y[None, :])
 ll = torch.empty(B, dtype=torch.float64, device="cuda"); info = torch.empty(B, dtype=torch.int32, device="cuda")
 ws, ws_bytes = eng.workspace(B, n)
+assert ws_bytes >= B * eng.matrix_stride(n) * 8, "batch does not fit the workspace"
 ld, stride = eng.ld(n), eng.matrix_stride(n)
 st = eng.stream()
 row_n = ctypes.c_void_p(ws.data_ptr() + n * ld * 8)
@@ -37,7 +38,7 @@ def sampler():
         except Exception:
             pass
         time.sleep(0.1)
-th = threading.Thread(target=sampler); th.start()
+th = threading.Thread(target=sampler, daemon=True); th.start()
 ms = []
 for rep in range(REPS):
     lib.mf_build_cov(h, ctypes.byref(prob), B, eng.ptr(t_d), eng.ptr(diag_d), eng.ptr(hyper_d), None, 2, eng.ptr(ws), ld, stride, st)
