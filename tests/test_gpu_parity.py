@@ -568,3 +568,25 @@ def test_lookahead_kernel_matches_plain_kernel(mf, N, tile):
     for b in ok[[0, ok.size // 2, -1]]:
         want = go.biggp_loglike_literal("SquaredExponential", A[b], t, y, e1, e2, e3)
         assert rel_err(float(ll2[b]), want) <= LL_RTOL
+
+
+def test_many_waves_hand_out(mf):
+    """More than four waves of small matrices: the persistent kernels hand the matrices out through
+    the atomic counter with no per-CTA limit (with fewer waves a CTA takes at most its share); every
+    sample is evaluated exactly once, reproducibly, and agrees with the oracle."""
+    N, B = 21, 3000
+    t, (rv, rhk, bis), (e1, e2, e3) = go.synthetic_series(N, seed=77)
+    gp = mf.BIGgp.BIGgp(mf.kernels.QuasiPeriodic, [None, None, None], t=t, rv=rv, rverr=e1, rhk=rhk,
+                        sig_rhk=e2, bis=bis, sig_bis=e3)
+    H = go.synthetic_biggp_hypers(B, seed=78)
+    a = np.asarray(gp.log_likelihood_batch(H))
+    b = np.asarray(gp.log_likelihood_batch(H))
+    assert a.shape == (B,) and np.all(np.isfinite(a)) and np.array_equal(a, b)
+    y = go.biggp_y(rv, rhk, bis)
+    for i in (0, 1, 443, 444, 445, B // 2, B - 2, B - 1):
+        want = go.biggp_loglike_literal("QuasiPeriodic", H[i], t, y, e1, e2, e3)
+        assert rel_err(float(a[i]), want) <= LL_RTOL
+    # the same samples in another order give the same values: no slot dependence
+    perm = np.random.default_rng(5).permutation(B)
+    c = np.asarray(gp.log_likelihood_batch(H[perm]))
+    assert np.array_equal(c, a[perm])
